@@ -1,0 +1,132 @@
+/* b200zk.h -- C ABI of the B200-native Groth16 / BLS12-381 prover backend.
+ *
+ * This is the drop-in boundary a Rust `-sys` crate (or cgo/ctypes) binds.  The reference
+ * tree (/root/reference, Cardinal-Cryptography/zk-apps @967d180) has NO prover-level API:
+ * its only first-party interface on this path is the circuit builder
+ *   update_note_circuit(ctx, UpdateNoteInput, make_public)
+ *     -- shielder/relations/src/relations/update_note.rs:106-149
+ * plus the Account/Operation traits (relations/src/account.rs:8-21, operation.rs:3-23).
+ * The entry points below are therefore shaped after the arkworks 0.4 call sites
+ * BASELINE.json names ([recall]): each function cites the arkworks
+ * item it replaces and, where one exists, the reference file that defines the semantics.
+ *
+ * Conventions (all functions):
+ *   - return 0 (B200ZK_OK) or a negative b200zk_status; b200zk_last_error(ctx) has the text;
+ *   - the caller owns every buffer; the library never frees caller memory and keeps no host
+ *     pointer after return; no exceptions cross the boundary;
+ *   - a ctx is single-threaded and bound to one GPU (one stream); use one ctx per thread;
+ *   - field elements are little-endian limbs in Montgomery form (a*R mod p, R = 2^256 for Fr,
+ *     2^384 for Fq) = the in-memory words of ark-ff 0.4 `Fp<MontBackend>`; MSM scalars are
+ *     canonical 256-bit little-endian integers = arkworks `BigInt<4>` (`into_bigint()`);
+ *   - G1 affine = x||y (96 B), G2 affine = x.c0||x.c1||y.c0||y.c1 (192 B); the point at
+ *     infinity is the all-zero encoding on input and output (plus an explicit flag where
+ *     stated); outputs are affine and fully reduced so byte comparison is meaningful;
+ *   - there is no CPU fallback: without a CUDA device b200zk_init fails.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_bases b200zk_bases;   /* device-resident MSM bases (proving-key query) */
+typedef struct b200zk_pk b200zk_pk;         /* device-resident Groth16 proving key + R1CS matrices */
+
+typedef enum {
+    B200ZK_OK = 0,
+    B200ZK_ERR_BAD_ARG = -1,
+    B200ZK_ERR_BAD_LEN = -2,          /* ark `msm` returns Err(len) on length mismatch */
+    B200ZK_ERR_DOMAIN_TOO_LARGE = -3, /* ark `Radix2EvaluationDomain::new` returns None if log2 > 32 */
+    B200ZK_ERR_CUDA = -4,
+    B200ZK_ERR_NO_DEVICE = -5,
+    B200ZK_ERR_UNSATISFIED = -6,      /* witness does not satisfy the relation (ark: SynthesisError::Unsatisfiable) */
+    B200ZK_ERR_NOT_IMPLEMENTED = -7
+} b200zk_status;
+
+enum { B200ZK_FIELD_FR = 0, B200ZK_FIELD_FQ = 1, B200ZK_FIELD_FQ2 = 2 };
+enum { B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQR = 3, B200ZK_OP_INV = 4,
+       B200ZK_OP_TO_MONT = 5, B200ZK_OP_FROM_MONT = 6 };
+
+/* ---- context ------------------------------------------------------------------------- */
+int b200zk_init(int device, b200zk_ctx** out);
+void b200zk_destroy(b200zk_ctx* ctx);
+const char* b200zk_last_error(b200zk_ctx* ctx);
+int b200zk_sync(b200zk_ctx* ctx);
+/* raw device memory for callers that keep operands resident in HBM */
+int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** dptr);
+int b200zk_dev_free(b200zk_ctx* ctx, void* dptr);
+int b200zk_dev_upload(b200zk_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int b200zk_dev_download(b200zk_ctx* ctx, void* host, const void* dptr, size_t bytes);
+/* the CUDA stream of the ctx (cudaStream_t), so callers can record their own events on it */
+void* b200zk_stream(b200zk_ctx* ctx);
+
+/* ---- profiling hooks (bench.py roofline leg) ----------------------------------------------
+ * With profiling enabled every launch of a tracked kernel family is bracketed by CUDA events on
+ * the ctx stream.  b200zk_prof_get syncs and returns the summed device milliseconds and launch
+ * count of `name` since the last reset.  b200zk_launch_count = all kernel launches of the ctx. */
+int b200zk_prof_enable(b200zk_ctx* ctx, int on);
+int b200zk_prof_reset(b200zk_ctx* ctx);
+int b200zk_prof_get(b200zk_ctx* ctx, const char* name, double* ms, long* launches);
+int b200zk_prof_names(b200zk_ctx* ctx, char* buf, size_t buflen);   /* comma-separated */
+long b200zk_launch_count(b200zk_ctx* ctx);
+
+/* ---- K1: field arithmetic test entry points ----------------------------------------------
+ * Element-wise out[i] = a[i] op b[i] on the GPU.  Replaces nothing in the reference (row a10);
+ * exists so the Montgomery kernels can be diffed against the oracle byte for byte. */
+int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
+                        uint8_t* out, size_t n);
+/* Integer-pipe micro-benchmarks: kind 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (mad.wide), 2 = Fr
+ * Montgomery mul, 3 = Fq Montgomery mul, 4 = DFMA.  Returns operations (IMADs, or field muls) per
+ * second sustained over all SMs -- the measured denominator of the integer roofline. */
+int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec);
+/* k_i * G for canonical scalars (fixed-base, used to make synthetic bases on the GPU):
+ * group 1 -> 96 B G1 affine each, group 2 -> 192 B G2 affine each; host buffers. */
+int b200zk_fixed_base_mul(b200zk_ctx* ctx, int group, const uint8_t* scalars, size_t n, uint8_t* out_points);
+/* same, device buffers (d_scalars n*32 B canonical, d_out n*96/192 B) */
+int b200zk_fixed_base_mul_device(b200zk_ctx* ctx, int group, const void* d_scalars, size_t n, void* d_out);
+
+/* ---- K2/K3: EvaluationDomain ------------------------------------------------------------
+ * Replaces ark_poly::Radix2EvaluationDomain::{fft_in_place, ifft_in_place} and the coset forms
+ * reached through get_coset(offset) (ark-poly 0.4.2 [recall]; absent from the reference, row a9).
+ * data: batch * 2^log_n Fr elements (Montgomery), natural order in and out, transformed in place.
+ *   forward:  X[k] = sum_j x[j] * offset^j * w^(jk)
+ *   inverse:  x[j] = offset^-j * n^-1 * sum_k X[k] * w^(-jk)
+ * coset_offset: 32 B Montgomery Fr, or NULL for offset 1.  log_n > 32 -> DOMAIN_TOO_LARGE
+ * (log_n above what fits device memory -> CUDA error).  The caller zero-pads to 2^log_n. */
+int b200zk_ntt_fr(b200zk_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse,
+                  const uint8_t* coset_offset, size_t batch);
+int b200zk_ntt_fr_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, int inverse,
+                         const uint8_t* coset_offset, size_t batch);
+
+/* ---- K4/K5: VariableBaseMSM ------------------------------------------------------------
+ * Replaces ark_ec::VariableBaseMSM::msm_bigint for G1Projective / G2Projective (ark-ec 0.4.2
+ * [recall]; absent from the reference, rows a7/a8).  sum_i scalars[i] * bases[i], result affine.
+ * inf_flags: n bytes (non-zero = base is the point at infinity) or NULL.
+ * b200zk_msm_* take host buffers; *_resident take bases uploaded once (optionally with the
+ * per-window multiples 2^(c*w) * P precomputed, which removes the window combine). */
+int b200zk_msm_g1(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags,
+                  const uint8_t* scalars, size_t n, uint8_t out_affine[96], uint8_t* out_is_inf);
+int b200zk_msm_g2(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags,
+                  const uint8_t* scalars, size_t n, uint8_t out_affine[192], uint8_t* out_is_inf);
+/* group: 1 = G1, 2 = G2.  precompute != 0 stores all window multiples (memory x windows). */
+int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8_t* inf_flags,
+                        size_t n, int precompute, b200zk_bases** out);
+/* wrap points already in device memory (affine, library layout); the library copies them */
+int b200zk_bases_from_device(b200zk_ctx* ctx, int group, const void* d_points, size_t n,
+                             int precompute, b200zk_bases** out);
+void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* h);
+/* batch MSMs sharing the bases: scalars = batch * n * 32 B (row b starts at b*n*32), out = batch
+ * affine points.  scalars_on_device != 0 means `scalars` is a device pointer. */
+int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars,
+                        int scalars_on_device, size_t n, size_t batch, uint8_t* out_affine,
+                        uint8_t* out_is_inf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

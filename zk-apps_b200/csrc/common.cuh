@@ -1,0 +1,127 @@
+// Host-side plumbing shared by every translation unit of libb200zk: the context behind the
+// C ABI (include/b200zk.h), error propagation without exceptions across the boundary, and a
+// small cache of device scratch buffers so steady-state calls never hit cudaMalloc.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+
+namespace b200zk {
+
+struct KernelTimer {  // CUDA-event timing of one named kernel family, summed over launches
+    double ms = 0.0;
+    long launches = 0;
+};
+
+struct DeviceBuf {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace b200zk
+
+struct b200zk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
+    std::map<uint64_t, b200zk::DeviceBuf> tables;          // twiddle / coset tables, keyed
+    // profiling (b200zk_prof_*): when enabled every launch of a tracked kernel is bracketed by
+    // events on ctx->stream; resolved lazily at b200zk_prof_get.
+    bool prof_enabled = false;
+    std::map<std::string, b200zk::KernelTimer> prof;
+    std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    long launches = 0;                                     // every kernel launch of this library
+    void* poseidon_consts = nullptr;                       // device copy, see poseidon.cu
+};
+
+namespace b200zk {
+
+inline int fail(b200zk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define B200ZK_CUDA(ctx, expr)                                                                  \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return ::b200zk::fail(ctx, B200ZK_ERR_CUDA,                                         \
+                                  std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + \
+                                      __FILE__ + ":" + std::to_string(__LINE__));               \
+    } while (0)
+
+#define B200ZK_TRY(expr)            \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != B200ZK_OK) return _rc; \
+    } while (0)
+
+// grow-only named scratch allocation
+inline int scratch(b200zk_ctx* ctx, const char* name, size_t bytes, void** out) {
+    DeviceBuf& b = ctx->scratch[name];
+    if (b.bytes < bytes) {
+        if (b.ptr) B200ZK_CUDA(ctx, cudaFree(b.ptr));
+        b.ptr = nullptr;
+        b.bytes = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&b.ptr, want);
+        if (e != cudaSuccess) {
+            want = bytes;
+            B200ZK_CUDA(ctx, cudaMalloc(&b.ptr, want));
+        }
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return B200ZK_OK;
+}
+
+inline int check_launch(b200zk_ctx* ctx, const char* what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(ctx, B200ZK_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return B200ZK_OK;
+}
+
+// RAII bracket used as:  { ProfScope p(ctx, "msm_accumulate"); kernel<<<...>>>(...); }
+struct ProfScope {
+    b200zk_ctx* ctx;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get_event(b200zk_ctx* ctx) {
+        if (!ctx->event_pool.empty()) {
+            cudaEvent_t e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(b200zk_ctx* c, const char* n) : ctx(c), name(n) {
+        if (ctx->prof_enabled) {
+            a = get_event(ctx);
+            b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~ProfScope() {
+        if (ctx->prof_enabled) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->prof_pending.emplace_back(name, a, b);
+        }
+    }
+};
+
+inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace b200zk

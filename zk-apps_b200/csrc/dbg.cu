@@ -1,0 +1,294 @@
+// K1 test kernels (element-wise field ops), integer-pipe micro-benchmarks that fix the
+// roofline denominator, and the fixed-base k*G kernel used to make synthetic MSM bases on
+// the device (2^24+ CPU scalar multiplications are infeasible).
+#include "common.cuh"
+#include "ec.cuh"
+
+using namespace b200zk;
+
+namespace {
+
+template <class F>
+__global__ void field_op_kernel(int op, const F* a, const F* b, F* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i];
+    F y = b ? b[i] : x;
+    F r;
+    switch (op) {
+        case B200ZK_OP_ADD: r = fp_add(x, y); break;
+        case B200ZK_OP_SUB: r = fp_sub(x, y); break;
+        case B200ZK_OP_MUL: r = fp_mul(x, y); break;
+        case B200ZK_OP_SQR: r = fp_sqr(x); break;
+        case B200ZK_OP_INV: r = fp_inv(x); break;
+        default: r = x; break;
+    }
+    out[i] = r;
+}
+
+template <class C>
+__global__ void mont_conv_kernel(int op, const Fp<C>* a, Fp<C>* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = op == B200ZK_OP_TO_MONT ? fp_to_mont(a[i]) : fp_from_mont(a[i]);
+}
+
+template <class F>
+int run_field_op(b200zk_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    size_t bytes = n * sizeof(F);
+    void *da, *db, *dout;
+    B200ZK_TRY(scratch(ctx, "dbg_a", bytes, &da));
+    B200ZK_TRY(scratch(ctx, "dbg_b", bytes, &db));
+    B200ZK_TRY(scratch(ctx, "dbg_o", bytes, &dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) B200ZK_CUDA(ctx, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    field_op_kernel<F><<<div_up(n, 128), 128, 0, ctx->stream>>>(op, (const F*)da, b ? (const F*)db : nullptr,
+                                                                (F*)dout, n);
+    B200ZK_TRY(check_launch(ctx, "field_op_kernel"));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+template <class C>
+int run_mont_conv(b200zk_ctx* ctx, int op, const uint8_t* a, uint8_t* out, size_t n) {
+    size_t bytes = n * sizeof(Fp<C>);
+    void *da, *dout;
+    B200ZK_TRY(scratch(ctx, "dbg_a", bytes, &da));
+    B200ZK_TRY(scratch(ctx, "dbg_o", bytes, &dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    mont_conv_kernel<C><<<div_up(n, 128), 128, 0, ctx->stream>>>(op, (const Fp<C>*)da, (Fp<C>*)dout, n);
+    B200ZK_TRY(check_launch(ctx, "mont_conv_kernel"));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+// ---------------------------------------------------------------- micro-benchmarks
+constexpr int PEAK_ITERS = 2048;
+
+__global__ void peak_imad32(uint32_t* out, uint32_t x, uint32_t y) {
+    uint32_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = threadIdx.x + k;
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(x), "r"(y));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+__global__ void peak_imad_wide(uint64_t* out, uint32_t x) {
+    uint64_t a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = threadIdx.x + k;
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t lo = (uint32_t)a[k];
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(lo), "r"(x));
+        }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= a[k];
+    if (s == 0x12345678ull) out[0] = s;
+}
+
+__global__ void peak_dfma(double* out, double x, double y) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = threadIdx.x + k;
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 0.123) out[0] = s;
+}
+
+template <class C>
+__global__ void peak_fpmul(Fp<C>* out, const Fp<C>* in) {
+    Fp<C> a = in[0], b = in[1];
+    a.v[0] ^= threadIdx.x;  // still < p for the inputs we pass (top limb untouched)
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        a = fp_mul(a, b);
+        b = fp_mul(b, a);
+    }
+    if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u) out[0] = a;
+}
+
+// ---------------------------------------------------------------- fixed-base multiplication
+template <class F>
+__global__ void fixed_base_kernel(const Affine<F>* gen, const uint32_t* scalars, size_t n, Affine<F>* out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = scalars[i * 8 + j];
+    Affine<F> g = *gen;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    // double-and-add with mixed additions of the affine generator
+    for (int limb = 7; limb >= 0; limb--)
+        for (int bit = 31; bit >= 0; bit--) {
+            acc = ec_dbl(acc);
+            if ((k[limb] >> bit) & 1) ec_madd(acc, g);
+        }
+    out[i] = ec_to_affine(acc);
+}
+
+// generators in Montgomery form are produced on the host from canonical constants (see gen_*)
+struct GenCache {
+    bool ready = false;
+    G1Affine g1;
+    G2Affine g2;
+};
+
+Fq fq_from_hex_be(const char* hex) {  // canonical big-endian hex (96 digits) -> Montgomery
+    Fq r = Fq::zero();
+    for (int i = 0; i < 96; i++) {
+        char c = hex[i];
+        uint32_t d = c <= '9' ? c - '0' : (c | 32) - 'a' + 10;
+        int bitpos = (95 - i) * 4;
+        r.v[bitpos / 32] |= d << (bitpos % 32);
+    }
+    return fp_to_mont(r);
+}
+
+const GenCache& generators() {
+    static GenCache g;
+    if (!g.ready) {
+        g.g1.x = fq_from_hex_be("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb");
+        g.g1.y = fq_from_hex_be("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1");
+        g.g2.x.c0 = fq_from_hex_be("024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8");
+        g.g2.x.c1 = fq_from_hex_be("13e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e");
+        g.g2.y.c0 = fq_from_hex_be("0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801");
+        g.g2.y.c1 = fq_from_hex_be("0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be");
+        g.ready = true;
+    }
+    return g;
+}
+
+template <class F>
+int fixed_base_device(b200zk_ctx* ctx, const Affine<F>& gen, const void* d_scalars, size_t n, void* d_out) {
+    void* dgen;
+    B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "gen_g1" : "gen_g2", sizeof(Affine<F>), &dgen));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dgen, &gen, sizeof(Affine<F>), cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `gen` may be a temporary
+    fixed_base_kernel<F><<<div_up(n, 64), 64, 0, ctx->stream>>>((const Affine<F>*)dgen, (const uint32_t*)d_scalars, n,
+                                                               (Affine<F>*)d_out);
+    return check_launch(ctx, "fixed_base_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
+                        size_t n) {
+    if (!ctx || !a || !out) return B200ZK_ERR_BAD_ARG;
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    bool conv = op == B200ZK_OP_TO_MONT || op == B200ZK_OP_FROM_MONT;
+    bool binary = op == B200ZK_OP_ADD || op == B200ZK_OP_SUB || op == B200ZK_OP_MUL;
+    if (binary && !b) return fail(ctx, B200ZK_ERR_BAD_ARG, "binary op needs b");
+    if (!binary) b = nullptr;
+    switch (field) {
+        case B200ZK_FIELD_FR: return conv ? run_mont_conv<FrCfg>(ctx, op, a, out, n) : run_field_op<Fr>(ctx, op, a, b, out, n);
+        case B200ZK_FIELD_FQ: return conv ? run_mont_conv<FqCfg>(ctx, op, a, out, n) : run_field_op<Fq>(ctx, op, a, b, out, n);
+        case B200ZK_FIELD_FQ2:
+            if (conv) return fail(ctx, B200ZK_ERR_BAD_ARG, "convert Fq2 as two Fq");
+            return run_field_op<Fq2>(ctx, op, a, b, out, n);
+        default: return fail(ctx, B200ZK_ERR_BAD_ARG, "unknown field");
+    }
+}
+
+int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {
+    if (!ctx || !ops_per_sec) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* dbuf;
+    B200ZK_TRY(scratch(ctx, "peak", 4096, &dbuf));
+    Fq two[2];
+    two[0] = Fq::one();
+    two[1] = fp_add(Fq::one(), Fq::one());
+    Fr twor[2];
+    twor[0] = Fr::one();
+    twor[1] = fp_add(Fr::one(), Fr::one());
+    if (kind == 2) B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, twor, sizeof(twor), cudaMemcpyHostToDevice, ctx->stream));
+    if (kind == 3) B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, two, sizeof(two), cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256;
+    const int blocks = ctx->sm_count * 8;
+    cudaEvent_t e0, e1;
+    B200ZK_CUDA(ctx, cudaEventCreate(&e0));
+    B200ZK_CUDA(ctx, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {  // rep 0 is the warm-up
+        B200ZK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        double ops = 0;
+        switch (kind) {
+            case 0:
+                peak_imad32<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)dbuf + 512, 3u + rep, 7u);
+                ops = 8.0 * PEAK_ITERS;
+                break;
+            case 1:
+                peak_imad_wide<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)dbuf + 256, 3u + rep);
+                ops = 8.0 * PEAK_ITERS;
+                break;
+            case 2:
+                peak_fpmul<FrCfg><<<blocks, threads, 0, ctx->stream>>>((Fr*)dbuf + 16, (const Fr*)dbuf);
+                ops = PEAK_ITERS;
+                break;
+            case 3:
+                peak_fpmul<FqCfg><<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = PEAK_ITERS;
+                break;
+            case 4:
+                peak_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)dbuf + 256, 1.0000001, 1e-9);
+                ops = 8.0 * PEAK_ITERS;
+                break;
+            default: return fail(ctx, B200ZK_ERR_BAD_ARG, "unknown kind");
+        }
+        B200ZK_TRY(check_launch(ctx, "peak kernel"));
+        B200ZK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        B200ZK_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        B200ZK_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        double rate = ops * threads * (double)blocks / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ops_per_sec = best;
+    return B200ZK_OK;
+}
+
+int b200zk_fixed_base_mul_device(b200zk_ctx* ctx, int group, const void* d_scalars, size_t n, void* d_out) {
+    if (!ctx || !d_scalars || !d_out) return B200ZK_ERR_BAD_ARG;
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (group == 1) return fixed_base_device<Fq>(ctx, generators().g1, d_scalars, n, d_out);
+    if (group == 2) return fixed_base_device<Fq2>(ctx, generators().g2, d_scalars, n, d_out);
+    return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+}
+
+int b200zk_fixed_base_mul(b200zk_ctx* ctx, int group, const uint8_t* scalars, size_t n, uint8_t* out_points) {
+    if (!ctx || !scalars || !out_points) return B200ZK_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+    if (n == 0) return B200ZK_OK;
+    size_t pt = group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    void *ds, *dout;
+    B200ZK_TRY(scratch(ctx, "fb_s", n * 32, &ds));
+    B200ZK_TRY(scratch(ctx, "fb_o", n * pt, &dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(b200zk_fixed_base_mul_device(ctx, group, ds, n, dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_points, dout, n * pt, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// K1 -- BLS12-381 Fr / Fq / Fq2 Montgomery arithmetic for sm_100a.
+//
+// No reference counterpart exists: /root/reference has no field arithmetic (SURVEY.md
+// section 8 row a10; it lives in lockfile-only halo2curves / ark-ff,
+// shielder/contract/Cargo.lock:224-225).  Representation = what ark-ff 0.4 stores:
+// little-endian limbs of a*R mod p with R = 2^(32*N) (N = 8 for Fr, 12 for Fq), so the
+// bit pattern equals arkworks' 64-bit-limb BigInt<4>/BigInt<6>.
+//
+// Device path: 32-bit mad.lo.cc / madc.hi.cc carry chains.  Each lo/hi pair on an
+// aligned register pair is one IMAD.WIDE.U32(.X) in SASS.  The running value is kept
+// split in two arrays X (register pairs at even limb positions) and Y (pairs at odd
+// positions), V = X + 2^32 * Y, so every 32x32 product lands on an aligned pair and no
+// carry chain is ever broken.  One b-limb per iteration: add a*b_i, add m*p with
+// m = X[0] * (-p^-1), shift right by one limb -- the shift swaps the roles of the two
+// arrays (pure register renaming); the single limb that changes parity (old X[1]) is
+// folded into new X[0] with one add.cc whose carry enters the next Y chain.
+// Host path (also used by the host-side constant generation): portable CIOS in C++.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+// out-of-line on purpose (code size / ptxas time); `inline` only for linkage
+#define HD_NOINLINE __host__ __device__ __noinline__ inline
+#else
+#define HD inline
+#define DEV inline
+#define HD_NOINLINE inline
+#endif
+
+namespace b200zk {
+
+// ------------------------------------------------------------------ field parameters
+struct FrCfg {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return m[i];
+    }
+    HD static constexpr uint32_t one(int i) {  // R mod r
+        constexpr uint32_t m[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return m[i];
+    }
+    HD static constexpr uint32_t r2(int i) {  // R^2 mod r
+        constexpr uint32_t m[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return m[i];
+    }
+};
+
+struct FqCfg {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu,
+                                    0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,
+                                    0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return m[i];
+    }
+    HD static constexpr uint32_t one(int i) {  // R mod p
+        constexpr uint32_t m[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu,
+                                    0x53c758bau, 0x5f489857u, 0x70525745u, 0x77ce5853u,
+                                    0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return m[i];
+    }
+    HD static constexpr uint32_t r2(int i) {  // R^2 mod p
+        constexpr uint32_t m[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u,
+                                    0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
+                                    0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return m[i];
+    }
+};
+
+// ------------------------------------------------------------------ PTX carry chains (generated)
+}  // namespace b200zk
+#include "field_asm.cuh"
+namespace b200zk {
+
+// ------------------------------------------------------------------ generic prime field element
+template <class C>
+struct alignas(16) Fp {
+    static constexpr int N = C::N;
+    using Cfg = C;
+    uint32_t v[N];
+
+    HD static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    HD static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = C::one(i);
+        return r;
+    }
+    HD static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = C::r2(i);
+        return r;
+    }
+    HD bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= v[i];
+        return o == 0;
+    }
+    HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    HD bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - p if a >= p else a   (a < 2p)
+template <class C>
+HD void fp_reduce_once(Fp<C>& a) {
+    constexpr int N = C::N;
+    uint32_t t[N];
+#if defined(__CUDA_ARCH__)
+    uint32_t pm[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) pm[i] = C::mod(i);
+    uint32_t borrow = ptx::sub_n<N>(t, a.v, pm);  // all-ones if a < p
+#pragma unroll
+    for (int i = 0; i < N; i++) a.v[i] = borrow ? a.v[i] : t[i];
+#else
+    uint64_t br = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t d = (uint64_t)a.v[i] - C::mod(i) - br;
+        t[i] = (uint32_t)d;
+        br = (d >> 63) & 1;
+    }
+    if (!br)
+        for (int i = 0; i < N; i++) a.v[i] = t[i];
+#endif
+}
+
+template <class C>
+HD Fp<C> fp_add(const Fp<C>& a, const Fp<C>& b) {
+    constexpr int N = C::N;
+    Fp<C> r;
+#if defined(__CUDA_ARCH__)
+    ptx::add_n<N>(r.v, a.v, b.v);  // 2p < 2^(32N): no carry out
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t s = (uint64_t)a.v[i] + b.v[i] + c;
+        r.v[i] = (uint32_t)s;
+        c = s >> 32;
+    }
+#endif
+    fp_reduce_once(r);
+    return r;
+}
+
+template <class C>
+HD Fp<C> fp_sub(const Fp<C>& a, const Fp<C>& b) {
+    constexpr int N = C::N;
+    Fp<C> r;
+#if defined(__CUDA_ARCH__)
+    uint32_t t[N], pm[N];
+    uint32_t borrow = ptx::sub_n<N>(t, a.v, b.v);  // all-ones if a < b
+#pragma unroll
+    for (int i = 0; i < N; i++) pm[i] = C::mod(i) & borrow;
+    ptx::add_n<N>(r.v, t, pm);
+#else
+    uint64_t br = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - br;
+        r.v[i] = (uint32_t)d;
+        br = (d >> 63) & 1;
+    }
+    if (br) {
+        uint64_t c = 0;
+        for (int i = 0; i < N; i++) {
+            uint64_t s = (uint64_t)r.v[i] + C::mod(i) + c;
+            r.v[i] = (uint32_t)s;
+            c = s >> 32;
+        }
+    }
+#endif
+    return r;
+}
+
+template <class C>
+HD Fp<C> fp_neg(const Fp<C>& a) {
+    return a.is_zero() ? a : fp_sub(Fp<C>::zero(), a);
+}
+
+template <class C>
+HD Fp<C> fp_dbl(const Fp<C>& a) { return fp_add(a, a); }
+
+// Montgomery product a*b/R mod p, fully reduced.  Inputs < p.
+template <class C>
+HD Fp<C> fp_mul(const Fp<C>& a, const Fp<C>& b) {
+    constexpr int N = C::N;
+    Fp<C> r;
+#if defined(__CUDA_ARCH__)
+    // V = X + 2^32 * Y.  X: limbs at positions 0..N, Y: limbs at positions 1..N.
+    uint32_t X[N + 1], Y[N], pm[N];
+#pragma unroll
+    for (int k = 0; k <= N; k++) X[k] = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) Y[k] = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) pm[k] = C::mod(k);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t bi = b.v[i];
+        if (i == 0) {
+            ptx::row_odd<N>(Y, a.v, bi);
+        } else {
+            // shift right one limb: X' = Y (+ old X[1] at position 0), Y' = X >> 64;
+            // the carry of Y[0] + X[1] enters the Y' chain (position 1) inside the same asm block
+            uint32_t nx[N + 1], ny[N];
+#pragma unroll
+            for (int k = 1; k < N; k++) nx[k] = Y[k];
+            nx[N] = 0;
+#pragma unroll
+            for (int k = 0; k < N - 1; k++) ny[k] = X[k + 2];
+            ny[N - 1] = 0;
+            ptx::row_odd_cin<N>(nx[0], Y[0], X[1], ny, a.v, bi);
+#pragma unroll
+            for (int k = 0; k <= N; k++) X[k] = nx[k];
+#pragma unroll
+            for (int k = 0; k < N; k++) Y[k] = ny[k];
+        }
+        ptx::row_even<N>(X, a.v, bi);
+        // m = X[0] * (-p^-1) mod 2^32;  V += m * p  (makes X[0] == 0)
+        const uint32_t m = X[0] * C::INV;
+        ptx::row_even<N>(X, pm, m);
+        ptx::row_odd<N>(Y, pm, m);
+    }
+    // V / 2^32 = Y + (X >> 32)
+    ptx::add_n<N>(r.v, Y, X + 1);
+#else
+    uint32_t t[N + 2];
+    for (int k = 0; k < N + 2; k++) t[k] = 0;
+    for (int i = 0; i < N; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < N; j++) {
+            uint64_t s = (uint64_t)a.v[j] * b.v[i] + t[j] + c;
+            t[j] = (uint32_t)s;
+            c = s >> 32;
+        }
+        uint64_t s = (uint64_t)t[N] + c;
+        t[N] = (uint32_t)s;
+        t[N + 1] = (uint32_t)(s >> 32);
+        uint32_t m = t[0] * C::INV;
+        s = (uint64_t)m * C::mod(0) + t[0];
+        c = s >> 32;
+        for (int j = 1; j < N; j++) {
+            s = (uint64_t)m * C::mod(j) + t[j] + c;
+            t[j - 1] = (uint32_t)s;
+            c = s >> 32;
+        }
+        s = (uint64_t)t[N] + c;
+        t[N - 1] = (uint32_t)s;
+        t[N] = t[N + 1] + (uint32_t)(s >> 32);
+    }
+    for (int k = 0; k < N; k++) r.v[k] = t[k];
+#endif
+    fp_reduce_once(r);
+    return r;
+}
+
+template <class C>
+HD Fp<C> fp_sqr(const Fp<C>& a) { return fp_mul(a, a); }
+
+template <class C>
+HD Fp<C> fp_to_mont(const Fp<C>& a) { return fp_mul(a, Fp<C>::r2()); }
+
+template <class C>
+HD Fp<C> fp_from_mont(const Fp<C>& a) {
+    Fp<C> o = Fp<C>::zero();
+    o.v[0] = 1;
+    return fp_mul(a, o);
+}
+
+// a^e for a little-endian limb exponent (not constant time; exponents here are public).
+template <class C>
+HD_NOINLINE Fp<C> fp_pow(const Fp<C>& a, const uint32_t* e, int nlimbs) {
+    Fp<C> r = Fp<C>::one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--) {
+        for (int bit = 31; bit >= 0; bit--) {
+            if (started) r = fp_sqr(r);
+            if ((e[i] >> bit) & 1) {
+                r = started ? fp_mul(r, a) : a;
+                started = true;
+            }
+        }
+    }
+    return r;
+}
+
+// a^(p-2); returns 0 for a == 0.
+template <class C>
+HD Fp<C> fp_inv(const Fp<C>& a) {
+    uint32_t e[C::N];
+    uint32_t borrow = 2;
+    for (int i = 0; i < C::N; i++) {  // p - 2
+        uint32_t m = C::mod(i);
+        e[i] = m - borrow;
+        borrow = (m < borrow) ? 1 : 0;
+    }
+    return fp_pow(a, e, C::N);
+}
+
+// a < b on the canonical (non-Montgomery) integer values given as limbs
+template <int N>
+HD bool limbs_gt(const uint32_t* a, const uint32_t* b) {
+    for (int i = N - 1; i >= 0; i--) {
+        if (a[i] > b[i]) return true;
+        if (a[i] < b[i]) return false;
+    }
+    return false;
+}
+
+using Fr = Fp<FrCfg>;
+using Fq = Fp<FqCfg>;
+
+// ------------------------------------------------------------------ Fq2 = Fq[u]/(u^2 + 1)
+struct alignas(16) Fq2 {
+    Fq c0, c1;
+    HD static Fq2 zero() { return Fq2{Fq::zero(), Fq::zero()}; }
+    HD static Fq2 one() { return Fq2{Fq::one(), Fq::zero()}; }
+    HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+};
+
+HD Fq2 fp_add(const Fq2& a, const Fq2& b) { return Fq2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+HD Fq2 fp_sub(const Fq2& a, const Fq2& b) { return Fq2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+HD Fq2 fp_neg(const Fq2& a) { return Fq2{fp_neg(a.c0), fp_neg(a.c1)}; }
+HD Fq2 fp_dbl(const Fq2& a) { return Fq2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
+// Fq2 products are out of line: a G2 accumulator does not fit the register file anyway, the
+// operands travel through L1-resident local memory (~2% of the product's issue time), and the
+// code shrinks ~10x (I-cache, ptxas time).
+HD_NOINLINE Fq2 fp_mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 Fq mul
+    Fq t0 = fp_mul(a.c0, b.c0);
+    Fq t1 = fp_mul(a.c1, b.c1);
+    Fq t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    return Fq2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+}
+HD_NOINLINE Fq2 fp_sqr(const Fq2& a) {  // (a0+a1)(a0-a1) + 2 a0 a1 u
+    Fq t0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
+    Fq t1 = fp_mul(a.c0, a.c1);
+    return Fq2{t0, fp_dbl(t1)};
+}
+HD Fq2 fp_inv(const Fq2& a) {
+    Fq d = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+    return Fq2{fp_mul(a.c0, d), fp_neg(fp_mul(a.c1, d))};
+}
+
+}  // namespace b200zk
