@@ -1,0 +1,118 @@
+"""K4/K5 parity (GPU): bucketed MSM over G1 and G2 vs the oracle, bit-exact affine bytes,
+through b200zk_msm_g1 / b200zk_msm_g2 / b200zk_msm_resident."""
+import numpy as np
+import pytest
+
+import zk_apps_b200 as z
+from oracle.pyref import bls12_381 as bls
+from oracle.pyref.algos import msm_pippenger
+from tests import util
+
+pytestmark = pytest.mark.gpu
+R = bls.R
+CURVES = {1: (bls.G1, util.g1_array, util.g1_list, 96), 2: (bls.G2, util.g2_array, util.g2_list, 192)}
+
+
+def _msm(ctx, group, bases, scalars, flags=None):
+    cv, enc, dec, pt = CURVES[group]
+    out, inf = z.VariableBaseMSM.msm_bigint(ctx, group, enc(bases), util.scalars_array(scalars), flags)
+    res = dec(out)[0]
+    assert inf == (res is None)
+    return res
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_kat(ctx, group):
+    """SURVEY.md Appendix A KATs: (1G..4G)x(1,2,3,4) = 30G ; (r-1,1,0,2) = 9G."""
+    cv = CURVES[group][0]
+    bases = [cv.mul(cv.gen, k) for k in (1, 2, 3, 4)]
+    assert _msm(ctx, group, bases, [1, 2, 3, 4]) == cv.mul(cv.gen, 30)
+    assert _msm(ctx, group, bases, [R - 1, 1, 0, 2]) == cv.mul(cv.gen, 9)
+    if group == 1:
+        assert bls.g1_compress(_msm(ctx, 1, bases, [1, 2, 3, 4])).hex().startswith("ad84464b3966ec5b")
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_edge_cases(ctx, group):
+    cv = CURVES[group][0]
+    g = cv.gen
+    p5, p7 = cv.mul(g, 5), cv.mul(g, 7)
+    assert _msm(ctx, group, [], []) is None                                   # empty
+    assert _msm(ctx, group, [p5, p7], [0, 0]) is None                          # all-zero scalars
+    assert _msm(ctx, group, [p5, cv.neg(p5)], [3, 3]) is None                  # P and -P cancel
+    assert _msm(ctx, group, [p5] * 6, [1] * 6) == cv.mul(g, 30)                # duplicate bases, equal scalars
+    assert _msm(ctx, group, [p5, p5, p7], [R - 1, R - 1, R - 1]) == cv.mul(g, (R - 1) * 17 % R)
+    assert _msm(ctx, group, [p5, None, p7], [2, 12345, 3]) == cv.mul(g, 31)    # infinity among the bases
+    flags = np.array([0, 1, 0], dtype=np.uint8)
+    assert _msm(ctx, group, [p5, p7, p7], [2, 12345, 3], flags) == cv.mul(g, 31)   # flagged infinity
+    with pytest.raises(z.B200zkError):                                          # ark msm: Err on length mismatch
+        z.VariableBaseMSM.msm_bigint(ctx, group, CURVES[group][1]([p5, p7]), util.scalars_array([1]))
+
+
+@pytest.mark.parametrize("group,n", [(1, 1), (1, 33), (1, 300), (2, 40)])
+def test_vs_oracle_pippenger(ctx, group, n):
+    """Same inputs into the oracle's arkworks-style bucket method (independent schedule)."""
+    cv = CURVES[group][0]
+    ks = util.rand_fr(7 + n, n)
+    bases = [cv.mul(cv.gen, k % 1000 + 1) for k in ks]
+    scalars = util.rand_fr(8 + n, n)
+    assert _msm(ctx, group, bases, scalars) == msm_pippenger(cv, bases, scalars)
+
+
+def _gpu_bases(ctx, group, seed, n):
+    ks = util.rand_fr_bytes_fast(seed, n)
+    pts = ctx.fixed_base_mul(group, ks)
+    return util.le_ints(ks), pts
+
+
+@pytest.mark.parametrize("group,log_n,precompute", [(1, 10, False), (1, 13, True), (1, 16, False), (1, 18, False),
+                                                    (2, 10, False), (2, 13, True), (2, 15, False)])
+def test_sum_identity(ctx, group, log_n, precompute):
+    """Exact full-size check: MSM(s, k*G) == (sum s_i k_i mod r) * G  (SURVEY.md section 8d)."""
+    cv, enc, dec, pt = CURVES[group]
+    n = 1 << log_n
+    ks, pts = _gpu_bases(ctx, group, 100 + log_n, n)
+    sbuf = util.rand_fr_bytes_fast(200 + log_n, n)
+    ss = util.le_ints(sbuf)
+    want = cv.mul(cv.gen, sum(a * b for a, b in zip(ks, ss)) % R)
+    h = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=precompute)
+    out, inf = h.msm(sbuf)
+    assert dec(out)[0] == want
+    if not precompute:
+        out2, _ = z.VariableBaseMSM.msm_bigint(ctx, group, pts, sbuf)
+        assert bytes(out2) == bytes(out)
+    h.free()
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_adversarial_distributions(ctx, group):
+    """Skewed scalars: all equal, all r-1, small (0/1-heavy like a Groth16 witness)."""
+    cv, enc, dec, pt = CURVES[group]
+    n = 1 << 11
+    ks, pts = _gpu_bases(ctx, group, 77, n)
+    ksum = sum(ks) % R
+    h = z.VariableBaseMSM.Bases(ctx, group, pts)
+    for s in (1, R - 1, 0x1234567, (1 << 254) + 12345):
+        out, _ = h.msm(util.scalars_array([s] * n))
+        assert dec(out)[0] == cv.mul(cv.gen, ksum * s % R)
+    rng = np.random.default_rng(3)
+    bits = [int(b) for b in rng.integers(0, 2, size=n)]
+    out, _ = h.msm(util.scalars_array(bits))
+    assert dec(out)[0] == cv.mul(cv.gen, sum(k for k, b in zip(ks, bits) if b) % R)
+    h.free()
+
+
+@pytest.mark.parametrize("group,precompute", [(1, False), (1, True), (2, True)])
+def test_batched_shared_bases(ctx, group, precompute):
+    """A batch of MSMs over the same bases (one per proof) in one pass."""
+    cv, enc, dec, pt = CURVES[group]
+    n, batch = 1 << 9, 5
+    ks, pts = _gpu_bases(ctx, group, 31, n)
+    h = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=precompute)
+    sbuf = util.rand_fr_bytes_fast(32, n * batch)
+    ss = util.le_ints(sbuf)
+    out, inf = h.msm(sbuf, n=n, batch=batch)
+    got = dec(out)
+    for b in range(batch):
+        assert got[b] == cv.mul(cv.gen, sum(k * s for k, s in zip(ks, ss[b * n:(b + 1) * n])) % R)
+    h.free()

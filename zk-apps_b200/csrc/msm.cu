@@ -1,0 +1,585 @@
+// K4/K5 -- bucketed (Pippenger) multi-scalar multiplication over G1 (Fq) and G2 (Fq2).
+//
+// Replaces ark_ec::VariableBaseMSM::msm_bigint (ark-ec 0.4.2 [recall]); absent from
+// /root/reference.  The result is a group element, so any
+// correct schedule yields the same affine bytes as arkworks' (App. B).
+//
+// Pipeline (all kernels below are ours; no CUB / thrust):
+//   1. msm_count:   signed c-bit digit decomposition of every scalar (digits in
+//                   [-2^(c-1), 2^(c-1)], so only 2^(c-1) buckets per window), histogram of
+//                   bucket keys  key = (msm_in_batch * windows + window) * 2^(c-1) + |d|-1
+//   2. scan_*:      exclusive prefix sum of the histogram (bucket start offsets)
+//   3. msm_scatter: counting-sort scatter of (point index | sign) into bucket order
+//   4. msm_accumulate: one thread per bucket, mixed additions (XYZZ += affine, 8M+2S) of the
+//                   bucket's points, 128-bit loads, next point prefetched while adding
+//   5. msm_chunk_reduce + msm_sum: weighted bucket sum  sum_j (j+1) B_j  per window by running
+//                   sums over 32-bucket chunks (+ one small scalar multiple per chunk), then a
+//                   log-depth tree of plain sums
+//   6. msm_finish:  Horner over windows (c doublings each) and conversion to affine.
+// With `precompute` bases (proving-key queries are fixed) the table holds 2^(c*w) * P_i for every
+// window, all windows share one bucket set, and step 6 has nothing to combine.
+// A batch of MSMs over the same bases (one per proof) is a single pass of this pipeline: the
+// msm index is just the high part of the bucket key.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "ec.cuh"
+
+using namespace b200zk;
+
+struct b200zk_bases {
+    int group = 0;           // 1 = G1, 2 = G2
+    size_t n = 0;            // points per window
+    void* d_points = nullptr;  // Affine<F>[n * (precomputed ? windows : 1)]
+    int precomputed = 0;
+    uint32_t c = 0, windows = 0;
+};
+
+namespace {
+
+struct Plan {
+    uint32_t c, windows, nb;      // nb = buckets per window = 2^(c-1)
+    uint32_t weff;                // bucket sets per msm: windows, or 1 when precomputed
+    bool precomp;
+};
+
+uint32_t pick_window(size_t n) {
+    if (const char* e = getenv("B200ZK_MSM_C")) {
+        int v = atoi(e);
+        if (v >= 2 && v <= 22) return (uint32_t)v;
+    }
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    int c = (int)lg - 4;
+    if (c < 3) c = 3;
+    if (c > 18) c = 18;
+    return (uint32_t)c;
+}
+
+Plan make_plan(size_t n, bool precomp, uint32_t c_fixed) {
+    Plan p;
+    p.c = c_fixed ? c_fixed : pick_window(n);
+    p.windows = (256 + p.c - 1) / p.c;
+    p.nb = 1u << (p.c - 1);
+    p.precomp = precomp;
+    p.weff = precomp ? 1 : p.windows;
+    return p;
+}
+
+// signed digit `w` of canonical scalar k; carry threads through successive calls (w ascending)
+__device__ __forceinline__ int32_t next_digit(const uint32_t* k, uint32_t w, uint32_t c, uint32_t& carry) {
+    const uint32_t bit = w * c;
+    uint32_t raw = 0;
+    if (bit < 256) {
+        const uint32_t limb = bit >> 5, sh = bit & 31;
+        raw = k[limb] >> sh;
+        if (sh + c > 32 && limb + 1 < 8) raw |= k[limb + 1] << (32 - sh);
+        raw &= (1u << c) - 1;
+    }
+    raw += carry;
+    if (raw > (1u << (c - 1))) {
+        carry = 1;
+        return (int32_t)raw - (int32_t)(1u << c);
+    }
+    carry = 0;
+    return (int32_t)raw;
+}
+
+__device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t idx, bool mont, uint32_t* k) {
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + idx * 8);
+    uint4 a = q[0], b = q[1];
+    Fr s;
+    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
+    s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+    if (mont) s = fp_from_mont(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = s.v[i];
+}
+
+// scalars: batch rows of n scalars, row stride `stride` elements
+__global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
+                          uint32_t* counts) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    const size_t b = t / n, i = t % n;
+    uint32_t k[8];
+    load_scalar(scalars, b * stride + i, mont != 0, k);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.windows; w++) {
+        int32_t d = next_digit(k, w, pl.c, carry);
+        if (d == 0) continue;
+        uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
+        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w)) * pl.nb + bucket;
+        atomicAdd(&counts[key], 1u);
+    }
+}
+
+__global__ void msm_scatter(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
+                            uint32_t* cursor, uint32_t* sorted) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    const size_t b = t / n, i = t % n;
+    uint32_t k[8];
+    load_scalar(scalars, b * stride + i, mont != 0, k);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.windows; w++) {
+        int32_t d = next_digit(k, w, pl.c, carry);
+        if (d == 0) continue;
+        uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
+        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w)) * pl.nb + bucket;
+        uint32_t pos = atomicAdd(&cursor[key], 1u);
+        uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * n + i : i);
+        sorted[pos] = pidx | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+
+// ---------------------------------------------------------------- exclusive scan (3 kernels)
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t prefix = wid ? warp_sums[wid - 1] : 0;
+    if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return prefix + x - v;
+}
+
+__global__ void scan_block_sums(const uint32_t* in, size_t n, uint32_t* block_sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) s += in[base + i];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of m values, running carry across chunks
+__global__ void scan_single(uint32_t* data, size_t m) {
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (size_t base = 0; base < m; base += SCAN_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < m ? data[i] : 0;
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        uint32_t c = carry_s;
+        if (i < m) data[i] = ex + c;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = c + total;
+        __syncthreads();
+    }
+}
+
+// out[i] = exclusive prefix of in; out[n] = total (written by the last block)
+__global__ void scan_apply(const uint32_t* in, size_t n, const uint32_t* block_offsets, uint32_t* out) {
+    size_t base = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total) + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = ex;
+        ex += v[i];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = ex;
+}
+
+// ---------------------------------------------------------------- point I/O
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
+    Affine<F> r;
+    constexpr int Q = sizeof(Affine<F>) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < Q; i++) dst[i] = __ldg(src + i);
+    return r;
+}
+
+// ---------------------------------------------------------------- bucket accumulation
+template <class F>
+__global__ void __launch_bounds__(128) msm_accumulate(const Affine<F>* __restrict__ bases,
+                                                      const uint32_t* __restrict__ offsets,
+                                                      const uint32_t* __restrict__ sorted, uint32_t n_keys,
+                                                      XYZZ<F>* __restrict__ buckets) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    uint32_t k = offsets[key];
+    const uint32_t end = offsets[key + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (k < end) {
+        uint32_t v = sorted[k];
+        Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
+        bool neg = (v >> 31) != 0;
+        for (k++; k < end; k++) {
+            uint32_t vn = sorted[k];
+            Affine<F> nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
+            ec_madd(acc, cur, neg);
+            cur = nxt;
+            neg = (vn >> 31) != 0;
+        }
+        ec_madd(acc, cur, neg);
+    }
+    buckets[key] = acc;
+}
+
+// ---------------------------------------------------------------- bucket reduction
+// chunk t of bucket set s covers buckets [t*S, (t+1)*S): out = sum_j (t*S + j + 1) * B_j
+template <class F>
+__global__ void __launch_bounds__(64) msm_chunk_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t nb,
+                                                       uint32_t log_s, uint32_t n_chunks_total,
+                                                       XYZZ<F>* __restrict__ out) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_chunks_total) return;
+    const uint32_t S = 1u << log_s;
+    const uint32_t chunks_per_set = nb >> log_s;
+    const uint32_t set = id / chunks_per_set, t = id % chunks_per_set;
+    const XYZZ<F>* B = buckets + (size_t)set * nb + (size_t)t * S;
+    XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
+    for (int j = (int)S - 1; j >= 0; j--) {
+        XYZZ<F> b = B[j];
+        ec_add(run, b);
+        ec_add(sum, run);
+    }
+    if (t) {
+        XYZZ<F> m = ec_mul_small(run, t << log_s);
+        ec_add(sum, m);
+    }
+    out[id] = sum;
+}
+
+// out[g][i] = sum of in[g][i*R .. i*R+R) ; m_in values per group
+template <class F>
+__global__ void __launch_bounds__(64) msm_sum(const XYZZ<F>* __restrict__ in, uint32_t groups, uint32_t m_in,
+                                              uint32_t R, XYZZ<F>* __restrict__ out) {
+    const uint32_t m_out = (m_in + R - 1) / R;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= groups * m_out) return;
+    const uint32_t g = id / m_out, i = id % m_out;
+    const XYZZ<F>* src = in + (size_t)g * m_in;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    const uint32_t hi = min(m_in, (i + 1) * R);
+    for (uint32_t j = i * R; j < hi; j++) {
+        XYZZ<F> b = src[j];
+        ec_add(acc, b);
+    }
+    out[id] = acc;
+}
+
+// window sums [batch][weff] -> affine result per msm
+template <class F>
+__global__ void __launch_bounds__(32) msm_finish(const XYZZ<F>* __restrict__ wsums, uint32_t batch, uint32_t weff,
+                                                 uint32_t c, Affine<F>* __restrict__ out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    XYZZ<F> acc = wsums[(size_t)b * weff + (weff - 1)];
+    for (int w = (int)weff - 2; w >= 0; w--) {
+        for (uint32_t d = 0; d < c; d++) acc = ec_dbl(acc);
+        XYZZ<F> s = wsums[(size_t)b * weff + w];
+        ec_add(acc, s);
+    }
+    out[b] = ec_to_affine(acc);
+}
+
+// table[w*n + i] = 2^c * table[(w-1)*n + i]
+template <class F>
+__global__ void __launch_bounds__(64) msm_precompute_step(const Affine<F>* __restrict__ prev, size_t n, uint32_t c,
+                                                          Affine<F>* __restrict__ next) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = XYZZ<F>::from_affine(load_affine(prev + i));
+    for (uint32_t d = 0; d < c; d++) p = ec_dbl(p);
+    next[i] = ec_to_affine(p);
+}
+
+template <class F>
+__global__ void apply_inf_flags(Affine<F>* pts, const uint8_t* flags, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) pts[i] = Affine<F>::inf();
+}
+
+int exclusive_scan(b200zk_ctx* ctx, const uint32_t* d_in, size_t n, uint32_t* d_out /* n+1 */) {
+    const unsigned blocks = div_up(n, SCAN_BLOCK);
+    void* bs;
+    B200ZK_TRY(scratch(ctx, "msm_scan_blocks", (size_t)blocks * 4 + 16, &bs));
+    scan_block_sums<<<blocks, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, (uint32_t*)bs);
+    B200ZK_TRY(check_launch(ctx, "scan_block_sums"));
+    scan_single<<<1, SCAN_THREADS, 0, ctx->stream>>>((uint32_t*)bs, blocks);
+    B200ZK_TRY(check_launch(ctx, "scan_single"));
+    scan_apply<<<blocks, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, (const uint32_t*)bs, d_out);
+    return check_launch(ctx, "scan_apply");
+}
+
+}  // namespace
+
+namespace b200zk {
+
+// Device-resident batched MSM.  d_scalars: batch rows (row stride `stride` Fr elements) of n
+// scalars, canonical or Montgomery (`mont`).  d_out: batch affine points.
+template <class F>
+int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride,
+               size_t batch, bool mont, Affine<F>* d_out) {
+    if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
+    if (batch == 0) return B200ZK_OK;
+    if (n == 0) {
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), ctx->stream));
+        return B200ZK_OK;
+    }
+    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0);
+    const uint64_t n_keys64 = (uint64_t)batch * pl.weff * pl.nb;
+    const uint64_t max_entries = (uint64_t)batch * n * pl.windows;
+    if (n_keys64 >= (1ull << 31) || max_entries >= (1ull << 32) || (uint64_t)h->n * pl.windows >= (1ull << 31))
+        return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit bucket keys; split the batch");
+    const uint32_t n_keys = (uint32_t)n_keys64;
+
+    void *d_counts, *d_offsets, *d_cursor, *d_sorted, *d_buckets, *d_red_a, *d_red_b;
+    B200ZK_TRY(scratch(ctx, "msm_counts", ((size_t)n_keys + 1) * 4, &d_counts));
+    B200ZK_TRY(scratch(ctx, "msm_offsets", ((size_t)n_keys + 1) * 4, &d_offsets));
+    B200ZK_TRY(scratch(ctx, "msm_cursor", ((size_t)n_keys + 1) * 4, &d_cursor));
+    B200ZK_TRY(scratch(ctx, "msm_sorted", (size_t)max_entries * 4, &d_sorted));
+    B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2",
+                       (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets));
+
+    const size_t total = n * batch;
+    B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, ctx->stream));
+    {
+        ProfScope ps(ctx, "msm_sort");
+        msm_count<<<div_up(total, 256), 256, 0, ctx->stream>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+                                                               (uint32_t*)d_counts);
+        B200ZK_TRY(check_launch(ctx, "msm_count"));
+        B200ZK_TRY(exclusive_scan(ctx, (const uint32_t*)d_counts, n_keys, (uint32_t*)d_offsets));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(d_cursor, d_offsets, (size_t)n_keys * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        msm_scatter<<<div_up(total, 256), 256, 0, ctx->stream>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+                                                                 (uint32_t*)d_cursor, (uint32_t*)d_sorted);
+        B200ZK_TRY(check_launch(ctx, "msm_scatter"));
+    }
+    {
+        ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2");
+        msm_accumulate<F><<<div_up(n_keys, 128), 128, 0, ctx->stream>>>((const Affine<F>*)h->d_points,
+                                                                        (const uint32_t*)d_offsets,
+                                                                        (const uint32_t*)d_sorted, n_keys,
+                                                                        (XYZZ<F>*)d_buckets);
+        B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
+    }
+    // bucket reduction
+    const uint32_t sets = (uint32_t)batch * pl.weff;
+    uint32_t log_s = 5;
+    while ((1u << log_s) > pl.nb) log_s--;
+    const uint32_t chunks_per_set = pl.nb >> log_s;
+    const uint32_t n_chunks = sets * chunks_per_set;
+    B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)n_chunks * sizeof(XYZZ<F>), &d_red_a));
+    B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)n_chunks / 8 + sets + 8) * sizeof(XYZZ<F>), &d_red_b));
+    {
+        ProfScope ps(ctx, "msm_reduce");
+        msm_chunk_reduce<F><<<div_up(n_chunks, 64), 64, 0, ctx->stream>>>((const XYZZ<F>*)d_buckets, pl.nb, log_s,
+                                                                           n_chunks, (XYZZ<F>*)d_red_a);
+        B200ZK_TRY(check_launch(ctx, "msm_chunk_reduce"));
+        uint32_t m = chunks_per_set;
+        XYZZ<F>* src = (XYZZ<F>*)d_red_a;
+        XYZZ<F>* dst = (XYZZ<F>*)d_red_b;
+        while (m > 1) {
+            const uint32_t R = 8;
+            const uint32_t m_out = (m + R - 1) / R;
+            msm_sum<F><<<div_up((size_t)sets * m_out, 64), 64, 0, ctx->stream>>>(src, sets, m, R, dst);
+            B200ZK_TRY(check_launch(ctx, "msm_sum"));
+            std::swap(src, dst);
+            m = m_out;
+        }
+        msm_finish<F><<<div_up(batch, 32), 32, 0, ctx->stream>>>(src, (uint32_t)batch, pl.weff, pl.c, d_out);
+        B200ZK_TRY(check_launch(ctx, "msm_finish"));
+    }
+    return B200ZK_OK;
+}
+
+template int msm_device<Fq>(b200zk_ctx*, const b200zk_bases*, const uint32_t*, size_t, size_t, size_t, bool,
+                            Affine<Fq>*);
+template int msm_device<Fq2>(b200zk_ctx*, const b200zk_bases*, const uint32_t*, size_t, size_t, size_t, bool,
+                             Affine<Fq2>*);
+
+template <class F>
+int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,
+                size_t n, int precompute) {
+    Plan pl = make_plan(n, precompute != 0, 0);
+    h->n = n;
+    h->precomputed = precompute ? 1 : 0;
+    h->c = pl.c;
+    h->windows = pl.windows;
+    const size_t copies = precompute ? pl.windows : 1;
+    B200ZK_CUDA(ctx, cudaMalloc(&h->d_points, std::max<size_t>(1, n * copies) * sizeof(Affine<F>)));
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(h->d_points, d_src, n * sizeof(Affine<F>),
+                                     src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (inf_flags) {
+        void* df;
+        B200ZK_TRY(scratch(ctx, "msm_inf", n, &df));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(df, inf_flags, n, cudaMemcpyHostToDevice, ctx->stream));
+        apply_inf_flags<F><<<div_up(n, 256), 256, 0, ctx->stream>>>((Affine<F>*)h->d_points, (const uint8_t*)df, n);
+        B200ZK_TRY(check_launch(ctx, "apply_inf_flags"));
+    }
+    if (precompute) {
+        Affine<F>* t = (Affine<F>*)h->d_points;
+        for (uint32_t w = 1; w < pl.windows; w++) {
+            msm_precompute_step<F><<<div_up(n, 64), 64, 0, ctx->stream>>>(t + (size_t)(w - 1) * n, n, pl.c,
+                                                                          t + (size_t)w * n);
+            B200ZK_TRY(check_launch(ctx, "msm_precompute_step"));
+        }
+    }
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host source buffers may go away
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk
+
+namespace {
+
+template <class F>
+int msm_host_entry(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8_t* inf_flags, const uint8_t* scalars,
+                   size_t n, uint8_t* out_affine, uint8_t* out_is_inf) {
+    if (!ctx || !out_affine || (n && (!bases || !scalars))) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_bases h;
+    h.group = group;
+    int rc = bases_build<F>(ctx, &h, (const Affine<F>*)bases, false, inf_flags, n, 0);
+    if (rc == B200ZK_OK) {
+        void *ds, *dout;
+        rc = scratch(ctx, "msm_scalars", std::max<size_t>(32, n * 32), &ds);
+        if (rc == B200ZK_OK) rc = scratch(ctx, "msm_out", sizeof(Affine<F>), &dout);
+        if (rc == B200ZK_OK && n)
+            if (cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+                rc = fail(ctx, B200ZK_ERR_CUDA, "scalar upload failed");
+        if (rc == B200ZK_OK) rc = msm_device<F>(ctx, &h, (const uint32_t*)ds, n, n, 1, false, (Affine<F>*)dout);
+        if (rc == B200ZK_OK) {
+            Affine<F> r;
+            if (cudaMemcpyAsync(&r, dout, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                rc = fail(ctx, B200ZK_ERR_CUDA, std::string("msm failed: ") + cudaGetErrorString(cudaGetLastError()));
+            else {
+                memcpy(out_affine, &r, sizeof(r));
+                if (out_is_inf) *out_is_inf = r.is_inf() ? 1 : 0;
+            }
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    if (h.d_points) cudaFree(h.d_points);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200zk_msm_g1(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags, const uint8_t* scalars, size_t n,
+                  uint8_t out_affine[96], uint8_t* out_is_inf) {
+    return msm_host_entry<Fq>(ctx, 1, bases, inf_flags, scalars, n, out_affine, out_is_inf);
+}
+
+int b200zk_msm_g2(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags, const uint8_t* scalars, size_t n,
+                  uint8_t out_affine[192], uint8_t* out_is_inf) {
+    return msm_host_entry<Fq2>(ctx, 2, bases, inf_flags, scalars, n, out_affine, out_is_inf);
+}
+
+int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8_t* inf_flags, size_t n,
+                        int precompute, b200zk_bases** out) {
+    if (!ctx || !out || (n && !bases)) return B200ZK_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_bases* h = new b200zk_bases();
+    h->group = group;
+    int rc = group == 1 ? bases_build<Fq>(ctx, h, (const Affine<Fq>*)bases, false, inf_flags, n, precompute)
+                        : bases_build<Fq2>(ctx, h, (const Affine<Fq2>*)bases, false, inf_flags, n, precompute);
+    if (rc != B200ZK_OK) {
+        if (h->d_points) cudaFree(h->d_points);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return B200ZK_OK;
+}
+
+int b200zk_bases_from_device(b200zk_ctx* ctx, int group, const void* d_points, size_t n, int precompute,
+                             b200zk_bases** out) {
+    if (!ctx || !out || (n && !d_points)) return B200ZK_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    b200zk_bases* h = new b200zk_bases();
+    h->group = group;
+    int rc = group == 1 ? bases_build<Fq>(ctx, h, (const Affine<Fq>*)d_points, true, nullptr, n, precompute)
+                        : bases_build<Fq2>(ctx, h, (const Affine<Fq2>*)d_points, true, nullptr, n, precompute);
+    if (rc != B200ZK_OK) {
+        if (h->d_points) cudaFree(h->d_points);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return B200ZK_OK;
+}
+
+void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* h) {
+    if (!h) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (h->d_points) cudaFree(h->d_points);
+    delete h;
+}
+
+int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars, int scalars_on_device, size_t n,
+                        size_t batch, uint8_t* out_affine, uint8_t* out_is_inf) {
+    if (!ctx || !h || !out_affine || (n && batch && !scalars)) return B200ZK_ERR_BAD_ARG;
+    if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pt = h->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    const uint32_t* ds = (const uint32_t*)scalars;
+    if (!scalars_on_device) {
+        void* d;
+        B200ZK_TRY(scratch(ctx, "msm_scalars", std::max<size_t>(32, n * batch * 32), &d));
+        if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(d, scalars, n * batch * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ds = (const uint32_t*)d;
+    }
+    void* dout;
+    B200ZK_TRY(scratch(ctx, "msm_out", batch * pt, &dout));
+    if (h->group == 1) B200ZK_TRY(msm_device<Fq>(ctx, h, ds, n, n, batch, false, (G1Affine*)dout));
+    else B200ZK_TRY(msm_device<Fq2>(ctx, h, ds, n, n, batch, false, (G2Affine*)dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine, dout, batch * pt, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_is_inf)
+        for (size_t b = 0; b < batch; b++) {
+            bool z = true;
+            for (size_t i = 0; i < pt; i++) z = z && out_affine[b * pt + i] == 0;
+            out_is_inf[b] = z ? 1 : 0;
+        }
+    return B200ZK_OK;
+}
+
+}  // extern "C"

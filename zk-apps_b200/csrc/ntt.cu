@@ -1,0 +1,365 @@
+// K2/K3 -- radix-2 Fr NTT / iNTT / coset NTT as a multi-pass "four-step" transform.
+//
+// Replaces ark_poly::Radix2EvaluationDomain::{fft,ifft}_in_place and the coset forms
+// (ark-poly 0.4.2 [recall]; absent from /root/reference -- SURVEY.md section 8 row a9).
+// Natural order in, natural order out, X[k] = sum_j x[j] w^(jk), w = 7^((r-1)/n).
+//
+// Decomposition (P passes, n = n_0 * n_1 * ... * n_{P-1}, each n_p <= 2^11):
+//   pass p views the data as [outer][n_p][inner] and runs, per CTA, G adjacent `inner` columns
+//   of the length-n_p transform entirely in shared memory (DIF radix-2 stages, inner twiddles
+//   staged in shared memory once per CTA), multiplies the result by the inter-pass twiddle
+//   w_M^(inner_idx * k), M = n_p * inner (fused into the store), and writes it back in place.
+//   The last pass has inner = 1 (rows are contiguous, fully coalesced loads) and scatters its
+//   outputs to the digit-reversed natural position, G consecutive rows per CTA so that the
+//   scattered stores are G*32 B contiguous.
+// One master table T[i] = w_n^i (i < n/2) per domain size serves every twiddle of every pass
+// (w_m^i = T[i * n/m], negation for the upper half, mirrored for the inverse).  Coset scaling is
+// fused into the first load (forward) or the last store (inverse, together with 1/n).
+//
+// HBM traffic: one read + one write of the vector per pass; arithmetic (n/2) log2 n butterfly
+// multiplications + n per pass boundary.  The kernel is bound by the integer pipe, not by HBM
+// (SURVEY.md section 0 item 4), both fractions are reported by bench.py.
+#include <cstring>
+
+#include "common.cuh"
+#include "field.cuh"
+
+using namespace b200zk;
+
+namespace {
+
+constexpr int MAX_LOG_LEN = 11;       // longest in-CTA transform
+constexpr int LOG_TILE = 11;          // elements per CTA tile (len * G)
+constexpr int NTT_THREADS = 512;
+constexpr int MAX_PASSES = 4;
+
+struct PassParams {
+    const Fr* in;
+    Fr* out;
+    const Fr* tw;          // master table, n/2 entries
+    const Fr* pre_scale;   // n entries or null (first pass, indexed by input position)
+    const Fr* post_scale;  // n entries or null (last pass, indexed by output position)
+    Fr n_inv;              // used when inverse && !post_scale
+    uint32_t log_n, log_len, log_inner, log_g;
+    uint32_t lg[MAX_PASSES];  // log sizes of all passes (for the output digit reversal)
+    uint32_t n_passes, pass;
+    uint32_t inverse;
+    uint64_t rows_total;   // last pass: batch * n / len
+};
+
+__device__ __forceinline__ Fr load_fr(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void store_fr(Fr* p, const Fr& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// shared memory keeps the two 16-byte halves of an element in separate arrays: a warp touching
+// consecutive elements then issues conflict-free LDS.128/STS.128
+__device__ __forceinline__ Fr sload(const uint4* lo, const uint4* hi, uint32_t i) {
+    Fr r;
+    uint4 a = lo[i], b = hi[i];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sstore(uint4* lo, uint4* hi, uint32_t i, const Fr& r) {
+    lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// w_n^E for E in [0, n), from the half table; `inverse` mirrors the exponent
+__device__ __forceinline__ Fr twiddle(const Fr* tw, uint32_t log_n, uint64_t E, bool inverse) {
+    const uint64_t n = 1ull << log_n;
+    if (inverse) E = (n - E) & (n - 1);
+    const uint64_t half = n >> 1;
+    if (E < half) return load_fr(tw + E);
+    return fp_neg(load_fr(tw + (E - half)));
+}
+
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t len = 1u << p.log_len, G = 1u << p.log_g, tile = len * G;
+    uint4* d_lo = smem;
+    uint4* d_hi = smem + tile;
+    uint4* t_lo = d_hi + tile;
+    uint4* t_hi = t_lo + (len >> 1);
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const bool last = p.pass + 1 == p.n_passes;
+    const bool inv = p.inverse != 0;
+    const uint64_t n = 1ull << p.log_n;
+
+    // ---- inner twiddles w_len^i, i < len/2
+    for (uint32_t i = tid; i < (len >> 1); i += T) {
+        Fr w = twiddle(p.tw, p.log_n, (uint64_t)i << (p.log_n - p.log_len), inv);
+        sstore(t_lo, t_hi, i, w);
+    }
+
+    // ---- tile geometry
+    uint64_t base = 0;       // non-last: element offset of (b, outer, r=0, inner0)
+    uint64_t inner0 = 0;     // non-last: first inner index of the tile
+    uint64_t row0 = 0;       // last: first row
+    const uint64_t t_id = blockIdx.x;
+    if (!last) {
+        const uint64_t tiles_per_slab = (1ull << p.log_inner) >> p.log_g;  // per (b, outer)
+        const uint64_t slab = t_id / tiles_per_slab;                       // = b * outer_count + outer
+        inner0 = (t_id % tiles_per_slab) << p.log_g;
+        base = (slab << (p.log_len + p.log_inner)) + inner0;
+    } else {
+        row0 = t_id << p.log_g;
+    }
+
+    // ---- load (smem index = r * G + g)
+    if (!last) {
+        for (uint32_t e = tid; e < tile; e += T) {
+            const uint32_t g = e & (G - 1), r = e >> p.log_g;
+            const uint64_t addr = base + ((uint64_t)r << p.log_inner) + g;
+            Fr x = load_fr(p.in + addr);
+            if (p.pre_scale) x = fp_mul(x, load_fr(p.pre_scale + (addr & (n - 1))));
+            sstore(d_lo, d_hi, e, x);
+        }
+    } else {
+        for (uint32_t e = tid; e < tile; e += T) {
+            const uint32_t r = e & (len - 1), g = e >> p.log_len;
+            const uint64_t row = row0 + g;
+            Fr x = Fr::zero();
+            if (row < p.rows_total) {
+                const uint64_t addr = (row << p.log_len) + r;
+                x = load_fr(p.in + addr);
+                if (p.pre_scale) x = fp_mul(x, load_fr(p.pre_scale + (addr & (n - 1))));
+            }
+            sstore(d_lo, d_hi, r * G + g, x);
+        }
+    }
+    __syncthreads();
+
+    // ---- DIF radix-2 stages
+    const uint32_t nb = tile >> 1;  // butterflies per stage
+    for (uint32_t s = 0; s < p.log_len; s++) {
+        const uint32_t log_half = p.log_len - 1 - s;
+        const uint32_t half = 1u << log_half;
+        for (uint32_t idx = tid; idx < nb; idx += T) {
+            const uint32_t g = idx & (G - 1), b = idx >> p.log_g;
+            const uint32_t j = b & (half - 1);
+            const uint32_t i0 = ((b >> log_half) << (log_half + 1)) + j;
+            const uint32_t e0 = i0 * G + g, e1 = (i0 + half) * G + g;
+            Fr u = sload(d_lo, d_hi, e0), v = sload(d_lo, d_hi, e1);
+            Fr a = fp_add(u, v);
+            Fr d = fp_sub(u, v);
+            if (half > 1 && j != 0) d = fp_mul(d, sload(t_lo, t_hi, j << s));
+            sstore(d_lo, d_hi, e0, a);
+            sstore(d_lo, d_hi, e1, d);
+        }
+        __syncthreads();
+    }
+
+    // ---- store: position q holds output k = bitrev(q)
+    const uint32_t rev_shift = 32 - p.log_len;
+    if (!last) {
+        const uint32_t log_m = p.log_len + p.log_inner;  // M = len * inner
+        for (uint32_t e = tid; e < tile; e += T) {
+            const uint32_t g = e & (G - 1), k = e >> p.log_g;
+            const uint32_t q = p.log_len ? (__brev(k) >> rev_shift) : 0;
+            Fr x = sload(d_lo, d_hi, q * G + g);
+            const uint64_t ex = (inner0 + g) * (uint64_t)k;  // < M
+            if (ex) x = fp_mul(x, twiddle(p.tw, p.log_n, ex << (p.log_n - log_m), inv));
+            store_fr(p.out + base + ((uint64_t)k << p.log_inner) + g, x);
+        }
+    } else {
+        const uint32_t log_rows = p.log_n - p.log_len;  // rows per transform
+        for (uint32_t e = tid; e < tile; e += T) {
+            const uint32_t g = e & (G - 1), k = e >> p.log_g;
+            const uint64_t row = row0 + g;
+            if (row >= p.rows_total) continue;
+            const uint64_t b = row >> log_rows;
+            uint64_t o = row & ((1ull << log_rows) - 1);
+            // digit reversal of o = ((k_0 n_1 + k_1) n_2 + ...) -> k_0 + n_0 k_1 + n_0 n_1 k_2 ...
+            uint64_t digits[MAX_PASSES];
+            for (int qd = (int)p.n_passes - 2; qd >= 0; qd--) {
+                digits[qd] = o & ((1ull << p.lg[qd]) - 1);
+                o >>= p.lg[qd];
+            }
+            uint64_t pos = 0;
+            uint32_t sh = 0;
+            for (uint32_t qd = 0; qd + 1 < p.n_passes; qd++) {
+                pos += digits[qd] << sh;
+                sh += p.lg[qd];
+            }
+            pos += (uint64_t)k << log_rows;
+            const uint32_t q = p.log_len ? (__brev(k) >> rev_shift) : 0;
+            Fr x = sload(d_lo, d_hi, q * G + g);
+            if (p.post_scale) x = fp_mul(x, load_fr(p.post_scale + pos));
+            else if (inv) x = fp_mul(x, p.n_inv);
+            store_fr(p.out + (b << p.log_n) + pos, x);
+        }
+    }
+}
+
+// out[i] = scale * base^i
+__global__ void pow_table_kernel(Fr base, Fr scale, Fr* out, uint64_t count) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t e[2] = {(uint32_t)i, (uint32_t)(i >> 32)};
+    Fr r = fp_pow(base, e, 2);
+    store_fr(out + i, fp_mul(r, scale));
+}
+
+const Fr& root_2_32() {  // 7^((r-1)/2^32), Montgomery form
+    static const Fr w = {{0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u,
+                          0x19e9b27bu, 0x5bf3addau}};
+    return w;
+}
+
+Fr host_root_of_unity(uint32_t log_n) {
+    Fr w = root_2_32();
+    for (uint32_t i = log_n; i < 32; i++) w = fp_sqr(w);
+    return w;
+}
+
+Fr host_fr_from_u64(uint64_t v) {
+    Fr r = Fr::zero();
+    r.v[0] = (uint32_t)v;
+    r.v[1] = (uint32_t)(v >> 32);
+    return fp_to_mont(r);
+}
+
+uint64_t hash_bytes(const uint8_t* b, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
+int get_table(b200zk_ctx* ctx, uint64_t key, const Fr& base, const Fr& scale, uint64_t count, const Fr** out) {
+    DeviceBuf& b = ctx->tables[key];
+    if (!b.ptr) {
+        size_t bytes = (size_t)(count ? count : 1) * sizeof(Fr);
+        B200ZK_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
+        b.bytes = bytes;
+        pow_table_kernel<<<div_up(count ? count : 1, 256), 256, 0, ctx->stream>>>(base, scale, (Fr*)b.ptr,
+                                                                                  count ? count : 1);
+        B200ZK_TRY(check_launch(ctx, "pow_table_kernel"));
+    }
+    *out = (const Fr*)b.ptr;
+    return B200ZK_OK;
+}
+
+}  // namespace
+
+namespace b200zk {
+
+// device-resident transform; used by the C ABI below and by the Groth16 pipeline
+int ntt_device(b200zk_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const Fr* coset_offset, size_t batch) {
+    if (log_n > 32) return fail(ctx, B200ZK_ERR_DOMAIN_TOO_LARGE, "log_n > 32");
+    if (batch == 0) return B200ZK_OK;
+    const uint64_t n = 1ull << log_n;
+    const bool coset = coset_offset && !(*coset_offset == Fr::one());
+    if (log_n == 0) return B200ZK_OK;  // n = 1: identity in every mode
+
+    const Fr w = host_root_of_unity(log_n);
+    const Fr* tw;
+    B200ZK_TRY(get_table(ctx, (1ull << 56) | log_n, w, Fr::one(), n >> 1, &tw));
+    const Fr n_inv = fp_inv(host_fr_from_u64(n));
+    const Fr *pre = nullptr, *post = nullptr;
+    if (coset) {
+        uint64_t h = hash_bytes((const uint8_t*)coset_offset, sizeof(Fr)) & 0x0000ffffffffff00ull;
+        if (!inverse) B200ZK_TRY(get_table(ctx, (2ull << 56) | h | log_n, *coset_offset, Fr::one(), n, &pre));
+        else B200ZK_TRY(get_table(ctx, (3ull << 56) | h | log_n, fp_inv(*coset_offset), n_inv, n, &post));
+    }
+
+    // plan
+    uint32_t P = (log_n + MAX_LOG_LEN - 1) / MAX_LOG_LEN;
+    if (P > MAX_PASSES) return fail(ctx, B200ZK_ERR_DOMAIN_TOO_LARGE, "too many passes");
+    uint32_t lg[MAX_PASSES] = {0, 0, 0, 0};
+    for (uint32_t q = 0; q < P; q++) lg[q] = log_n / P + (q < log_n % P ? 1 : 0);
+
+    Fr* tmp = nullptr;
+    if (P > 1) {
+        void* t;
+        B200ZK_TRY(scratch(ctx, "ntt_tmp", batch * n * sizeof(Fr), &t));
+        tmp = (Fr*)t;
+    }
+    const int max_smem = (int)(((1u << LOG_TILE) + (1u << (MAX_LOG_LEN - 1))) * 32);
+    B200ZK_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+
+    uint32_t log_inner = log_n;
+    for (uint32_t q = 0; q < P; q++) {
+        log_inner -= lg[q];
+        PassParams p;
+        p.in = (q == 0) ? d_data : tmp;
+        p.out = (q + 1 == P) ? d_data : tmp;
+        p.tw = tw;
+        p.pre_scale = q == 0 ? pre : nullptr;
+        p.post_scale = q + 1 == P ? post : nullptr;
+        p.n_inv = n_inv;
+        p.log_n = log_n;
+        p.log_len = lg[q];
+        p.log_inner = log_inner;
+        for (int i = 0; i < MAX_PASSES; i++) p.lg[i] = lg[i];
+        p.n_passes = P;
+        p.pass = q;
+        p.inverse = inverse ? 1 : 0;
+        const bool last = q + 1 == P;
+        uint64_t tiles;
+        if (!last) {
+            uint32_t lgG = LOG_TILE - lg[q];
+            if (lgG > log_inner) lgG = log_inner;
+            p.log_g = lgG;
+            p.rows_total = 0;
+            tiles = (uint64_t)batch << (log_n - lg[q] - lgG);
+        } else {
+            uint64_t rows = (uint64_t)batch << (log_n - lg[q]);
+            uint32_t lgG = LOG_TILE - lg[q];
+            while (lgG > 0 && (1ull << lgG) > rows) lgG--;
+            // keep G within one transform's rows unless the transform is a single row
+            if (log_n - lg[q] > 0 && lgG > log_n - lg[q]) lgG = log_n - lg[q];
+            p.log_g = lgG;
+            p.rows_total = rows;
+            tiles = (rows + (1ull << lgG) - 1) >> lgG;
+        }
+        if (tiles > 0x7fffffffull) return fail(ctx, B200ZK_ERR_BAD_ARG, "NTT grid too large");
+        const size_t smem = (size_t)(((1u << (lg[q] + p.log_g)) + ((1u << lg[q]) >> 1)) * 32);
+        {
+            ProfScope ps(ctx, "ntt_pass");
+            ntt_pass_kernel<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(p);
+        }
+        B200ZK_TRY(check_launch(ctx, "ntt_pass_kernel"));
+    }
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk
+
+extern "C" {
+
+int b200zk_ntt_fr_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, int inverse, const uint8_t* coset_offset,
+                         size_t batch) {
+    if (!ctx || !d_data) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr off;
+    if (coset_offset) memcpy(&off, coset_offset, sizeof(Fr));
+    return ntt_device(ctx, (Fr*)d_data, log_n, inverse != 0, coset_offset ? &off : nullptr, batch);
+}
+
+int b200zk_ntt_fr(b200zk_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, const uint8_t* coset_offset,
+                  size_t batch) {
+    if (!ctx || !data) return B200ZK_ERR_BAD_ARG;
+    if (log_n > 32) return fail(ctx, B200ZK_ERR_DOMAIN_TOO_LARGE, "log_n > 32");
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t bytes = (batch << log_n) * sizeof(Fr);
+    void* d;
+    B200ZK_TRY(scratch(ctx, "ntt_io", bytes, &d));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(b200zk_ntt_fr_device(ctx, d, log_n, inverse, coset_offset, batch));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+}  // extern "C"

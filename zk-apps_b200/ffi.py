@@ -1,0 +1,290 @@
+"""ctypes binding of include/b200zk.h plus thin arkworks-shaped wrappers.
+
+Names follow the arkworks 0.4 items this backend replaces ([recall]):
+  ark_ec::VariableBaseMSM::{msm, msm_bigint}            -> VariableBaseMSM.msm_bigint
+  ark_poly::Radix2EvaluationDomain::{new, fft_in_place,
+      ifft_in_place, get_coset}                         -> Radix2EvaluationDomain
+Buffers are plain bytes / numpy uint8 arrays in the layouts include/b200zk.h documents.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+FR_BYTES, FQ_BYTES, G1_BYTES, G2_BYTES = 32, 48, 96, 192
+R_MOD = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+_FR_R = pow(2, 256, R_MOD)
+_FR_RINV = pow(_FR_R, -1, R_MOD)
+
+STATUS = {0: "OK", -1: "BAD_ARG", -2: "BAD_LEN", -3: "DOMAIN_TOO_LARGE", -4: "CUDA", -5: "NO_DEVICE",
+          -6: "UNSATISFIED", -7: "NOT_IMPLEMENTED"}
+
+
+class B200zkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("b200zk %s (%d): %s" % (STATUS.get(code, "?"), code, msg))
+        self.code = code
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200zk.so")
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200zk.so.  No fallback: a missing library is an error, not a reason to go slow."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise B200zkError(-5, "libb200zk.so not built (run `python __graft_entry__.py` / build())")
+        L = C.CDLL(p)
+        vp, sz, u8p, i32, u32 = C.c_void_p, C.c_size_t, C.c_char_p, C.c_int, C.c_uint32
+        sig = {
+            "b200zk_init": (i32, [i32, C.POINTER(vp)]),
+            "b200zk_destroy": (None, [vp]),
+            "b200zk_last_error": (C.c_char_p, [vp]),
+            "b200zk_sync": (i32, [vp]),
+            "b200zk_dev_alloc": (i32, [vp, sz, C.POINTER(vp)]),
+            "b200zk_dev_free": (i32, [vp, vp]),
+            "b200zk_dev_upload": (i32, [vp, vp, vp, sz]),
+            "b200zk_dev_download": (i32, [vp, vp, vp, sz]),
+            "b200zk_stream": (vp, [vp]),
+            "b200zk_prof_enable": (i32, [vp, i32]),
+            "b200zk_prof_reset": (i32, [vp]),
+            "b200zk_prof_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+            "b200zk_prof_names": (i32, [vp, C.c_char_p, sz]),
+            "b200zk_launch_count": (C.c_long, [vp]),
+            "b200zk_dbg_field_op": (i32, [vp, i32, i32, vp, vp, vp, sz]),
+            "b200zk_dbg_int_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
+            "b200zk_fixed_base_mul": (i32, [vp, i32, vp, sz, vp]),
+            "b200zk_fixed_base_mul_device": (i32, [vp, i32, vp, sz, vp]),
+            "b200zk_ntt_fr": (i32, [vp, vp, u32, i32, vp, sz]),
+            "b200zk_ntt_fr_device": (i32, [vp, vp, u32, i32, vp, sz]),
+            "b200zk_msm_g1": (i32, [vp, vp, vp, vp, sz, vp, vp]),
+            "b200zk_msm_g2": (i32, [vp, vp, vp, vp, sz, vp, vp]),
+            "b200zk_bases_upload": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),
+            "b200zk_bases_from_device": (i32, [vp, i32, vp, sz, i32, C.POINTER(vp)]),
+            "b200zk_bases_free": (None, [vp, vp]),
+            "b200zk_msm_resident": (i32, [vp, vp, vp, i32, sz, sz, vp, vp]),
+        }
+        for name, (res, args) in sig.items():
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _buf(x):
+    """bytes / bytearray / numpy array -> (ctypes pointer, keepalive)"""
+    if x is None:
+        return None, None
+    if isinstance(x, np.ndarray):
+        a = np.ascontiguousarray(x)
+        return a.ctypes.data_as(C.c_void_p), a
+    if isinstance(x, (bytes, bytearray)):
+        a = np.frombuffer(x, dtype=np.uint8)
+        return a.ctypes.data_as(C.c_void_p), a
+    raise TypeError(type(x))
+
+
+def fr_to_mont(v: int) -> bytes:
+    return (v % R_MOD * _FR_R % R_MOD).to_bytes(32, "little")
+
+
+def fr_from_mont(b: bytes) -> int:
+    return int.from_bytes(b, "little") * _FR_RINV % R_MOD
+
+
+class Context:
+    """One GPU, one stream (b200zk_ctx).  Single-threaded, like the C ABI says."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().b200zk_init(device, C.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise B200zkError(rc, "b200zk_init failed (no CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().b200zk_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise B200zkError(rc, lib().b200zk_last_error(self._h).decode(errors="replace"))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        self.check(lib().b200zk_sync(self._h))
+
+    # ---- device memory
+    def alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self.check(lib().b200zk_dev_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr: int):
+        self.check(lib().b200zk_dev_free(self._h, C.c_void_p(dptr)))
+
+    def upload(self, dptr: int, data):
+        p, keep = _buf(data)
+        self.check(lib().b200zk_dev_upload(self._h, C.c_void_p(dptr), p, keep.nbytes))
+
+    def download(self, dptr: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        self.check(lib().b200zk_dev_download(self._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(dptr), nbytes))
+        return out
+
+    # ---- profiling
+    def prof_enable(self, on: bool = True):
+        self.check(lib().b200zk_prof_enable(self._h, 1 if on else 0))
+
+    def prof_reset(self):
+        self.check(lib().b200zk_prof_reset(self._h))
+
+    def prof_get(self, name: str):
+        ms, n = C.c_double(), C.c_long()
+        self.check(lib().b200zk_prof_get(self._h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def prof_names(self):
+        buf = C.create_string_buffer(4096)
+        self.check(lib().b200zk_prof_names(self._h, buf, 4096))
+        return [s for s in buf.value.decode().split(",") if s]
+
+    def launch_count(self) -> int:
+        return lib().b200zk_launch_count(self._h)
+
+    # ---- K1 debug
+    def field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
+        size = (32, 48, 96)[field]
+        pa, ka = _buf(a)
+        pb, kb = _buf(b)
+        n = ka.nbytes // size
+        out = np.empty(n * size, dtype=np.uint8)
+        self.check(lib().b200zk_dbg_field_op(self._h, field, op, pa, pb, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def int_peak(self, kind: int) -> float:
+        v = C.c_double()
+        self.check(lib().b200zk_dbg_int_peak(self._h, kind, C.byref(v)))
+        return v.value
+
+    def fixed_base_mul(self, group: int, scalars) -> np.ndarray:
+        ps, ks = _buf(scalars)
+        n = ks.nbytes // 32
+        out = np.empty(n * (G1_BYTES if group == 1 else G2_BYTES), dtype=np.uint8)
+        self.check(lib().b200zk_fixed_base_mul(self._h, group, ps, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+class VariableBaseMSM:
+    """ark_ec::VariableBaseMSM for G1Projective (group=1) / G2Projective (group=2)."""
+
+    @staticmethod
+    def msm_bigint(ctx: Context, group: int, bases, scalars, inf_flags=None):
+        """-> (affine bytes, is_infinity).  Like ark `msm`: a length mismatch is an error."""
+        pt = G1_BYTES if group == 1 else G2_BYTES
+        pb, kb = _buf(bases)
+        ps, ks = _buf(scalars)
+        pf, kf = _buf(inf_flags)
+        n = kb.nbytes // pt if kb is not None else 0
+        if ks is None or ks.nbytes // 32 != n:
+            raise B200zkError(-2, "bases/scalars length mismatch")
+        out = np.zeros(pt, dtype=np.uint8)
+        inf = C.c_uint8()
+        fn = lib().b200zk_msm_g1 if group == 1 else lib().b200zk_msm_g2
+        ctx.check(fn(ctx.handle, pb, pf, ps, n, out.ctypes.data_as(C.c_void_p), C.byref(inf)))
+        return out.tobytes(), bool(inf.value)
+
+    class Bases:
+        """Device-resident bases (a proving-key query); precompute=True stores all window multiples."""
+
+        def __init__(self, ctx: Context, group: int, bases=None, inf_flags=None, precompute: bool = False,
+                     device_ptr: int | None = None, n: int | None = None):
+            self.ctx, self.group = ctx, group
+            self._h = C.c_void_p()
+            pt = G1_BYTES if group == 1 else G2_BYTES
+            if device_ptr is not None:
+                self.n = n
+                ctx.check(lib().b200zk_bases_from_device(ctx.handle, group, C.c_void_p(device_ptr), n,
+                                                         1 if precompute else 0, C.byref(self._h)))
+            else:
+                pb, kb = _buf(bases)
+                pf, kf = _buf(inf_flags)
+                self.n = kb.nbytes // pt
+                ctx.check(lib().b200zk_bases_upload(ctx.handle, group, pb, pf, self.n, 1 if precompute else 0,
+                                                    C.byref(self._h)))
+
+        def msm(self, scalars=None, n: int | None = None, batch: int = 1, device_ptr: int | None = None):
+            pt = G1_BYTES if self.group == 1 else G2_BYTES
+            out = np.zeros(batch * pt, dtype=np.uint8)
+            inf = np.zeros(batch, dtype=np.uint8)
+            if device_ptr is not None:
+                ps, on_dev = C.c_void_p(device_ptr), 1
+            else:
+                ps, ks = _buf(scalars)
+                on_dev = 0
+                if n is None:
+                    n = ks.nbytes // 32 // batch
+            self.ctx.check(lib().b200zk_msm_resident(self.ctx.handle, self._h, ps, on_dev, n, batch,
+                                                     out.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p)))
+            return out, inf
+
+        def free(self):
+            if self._h:
+                lib().b200zk_bases_free(self.ctx.handle, self._h)
+                self._h = None
+
+        __del__ = free
+
+
+class Radix2EvaluationDomain:
+    """ark_poly::Radix2EvaluationDomain<Fr>.  `new` returns None when log2(size) > 32, as arkworks does."""
+
+    def __init__(self, ctx: Context, log_size: int, offset: bytes | None = None):
+        self.ctx, self.log_size, self.size, self.offset = ctx, log_size, 1 << log_size, offset
+
+    @classmethod
+    def new(cls, ctx: Context, num_coeffs: int):
+        log = max(0, (num_coeffs - 1).bit_length())
+        if log > 32:
+            return None
+        return cls(ctx, log)
+
+    def get_coset(self, offset_mont: bytes) -> "Radix2EvaluationDomain":
+        return Radix2EvaluationDomain(self.ctx, self.log_size, bytes(offset_mont))
+
+    def _run(self, data, inverse: bool, batch: int):
+        a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data)
+        a = a.copy()
+        want = batch * self.size * FR_BYTES
+        if a.nbytes < want:                                  # arkworks zero-pads to the domain size
+            a = np.concatenate([a, np.zeros(want - a.nbytes, dtype=np.uint8)])
+        off, keep = _buf(self.offset)
+        self.ctx.check(lib().b200zk_ntt_fr(self.ctx.handle, a.ctypes.data_as(C.c_void_p), self.log_size,
+                                           1 if inverse else 0, off, batch))
+        return a
+
+    def fft(self, coeffs, batch: int = 1) -> np.ndarray:
+        return self._run(coeffs, False, batch)
+
+    def ifft(self, evals, batch: int = 1) -> np.ndarray:
+        return self._run(evals, True, batch)
+
+    def fft_device(self, dptr: int, inverse: bool = False, batch: int = 1):
+        off, keep = _buf(self.offset)
+        self.ctx.check(lib().b200zk_ntt_fr_device(self.ctx.handle, C.c_void_p(dptr), self.log_size,
+                                                  1 if inverse else 0, off, batch))
