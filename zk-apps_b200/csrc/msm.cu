@@ -226,30 +226,112 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 }
 
 // ---------------------------------------------------------------- bucket accumulation
+// Buckets are cut into tasks of at most TASK_LEN entries so that one huge bucket (the top window
+// of any scalar distribution, 0/1-heavy witnesses, adversarial inputs) cannot serialise the
+// kernel.  A bucket with one task is written straight to `buckets`; the partial sums of a
+// multi-task bucket go to `partials` and are folded by msm_fold_small / msm_fold_big.
+constexpr uint32_t LOG_TASK_LEN = 8, TASK_LEN = 1u << LOG_TASK_LEN;
+constexpr uint32_t FOLD_SMALL_MAX = 8;
+
+__global__ void msm_task_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t* __restrict__ tcount) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    uint32_t cnt = offsets[key + 1] - offsets[key];
+    tcount[key] = (cnt + TASK_LEN - 1) >> LOG_TASK_LEN;
+}
+
+__global__ void msm_task_list(const uint32_t* __restrict__ toff, uint32_t n_keys, uint32_t* __restrict__ tasks) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    const uint32_t lo = toff[key], hi = toff[key + 1];
+    for (uint32_t t = lo; t < hi; t++) tasks[t] = key;
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const Affine<F>* __restrict__ bases,
                                                       const uint32_t* __restrict__ offsets,
-                                                      const uint32_t* __restrict__ sorted, uint32_t n_keys,
-                                                      XYZZ<F>* __restrict__ buckets) {
+                                                      const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ toff,
+                                                      const uint32_t* __restrict__ tasks, uint32_t n_tasks,
+                                                      XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ partials) {
+    uint32_t task = blockIdx.x * blockDim.x + threadIdx.x;
+    if (task >= n_tasks) return;
+    const uint32_t key = tasks[task];
+    const uint32_t t0 = toff[key], nt = toff[key + 1] - t0;
+    uint32_t k = offsets[key] + ((task - t0) << LOG_TASK_LEN);
+    const uint32_t end = min(k + TASK_LEN, offsets[key + 1]);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t v = sorted[k];
+    Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
+    bool neg = (v >> 31) != 0;
+    for (k++; k < end; k++) {
+        uint32_t vn = sorted[k];
+        Affine<F> nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
+        ec_madd(acc, cur, neg);
+        cur = nxt;
+        neg = (vn >> 31) != 0;
+    }
+    ec_madd(acc, cur, neg);
+    if (nt == 1) buckets[key] = acc;
+    else partials[task] = acc;
+}
+
+// thread per bucket: empty -> infinity, <= FOLD_SMALL_MAX partials -> summed here, more -> queued
+template <class F>
+__global__ void __launch_bounds__(64) msm_fold_small(const uint32_t* __restrict__ toff, uint32_t n_keys,
+                                                     const XYZZ<F>* __restrict__ partials,
+                                                     XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ big_list,
+                                                     uint32_t* __restrict__ big_count) {
     uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
-    uint32_t k = offsets[key];
-    const uint32_t end = offsets[key + 1];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    if (k < end) {
-        uint32_t v = sorted[k];
-        Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
-        bool neg = (v >> 31) != 0;
-        for (k++; k < end; k++) {
-            uint32_t vn = sorted[k];
-            Affine<F> nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
-            ec_madd(acc, cur, neg);
-            cur = nxt;
-            neg = (vn >> 31) != 0;
-        }
-        ec_madd(acc, cur, neg);
+    const uint32_t lo = toff[key], nt = toff[key + 1] - lo;
+    if (nt == 1) return;
+    if (nt == 0) {
+        buckets[key] = XYZZ<F>::inf();
+        return;
+    }
+    if (nt > FOLD_SMALL_MAX) {
+        big_list[atomicAdd(big_count, 1u)] = key;
+        return;
+    }
+    XYZZ<F> acc = partials[lo];
+    for (uint32_t t = 1; t < nt; t++) {
+        XYZZ<F> b = partials[lo + t];
+        ec_add(acc, b);
     }
     buckets[key] = acc;
+}
+
+// one warp per queued bucket: lanes stride over the partials, then a shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(32) msm_fold_big(const uint32_t* __restrict__ toff,
+                                                   const XYZZ<F>* __restrict__ partials,
+                                                   XYZZ<F>* __restrict__ buckets,
+                                                   const uint32_t* __restrict__ big_list,
+                                                   const uint32_t* __restrict__ big_count) {
+    __shared__ XYZZ<F> sh[32];
+    for (uint32_t item = blockIdx.x; item < *big_count; item += gridDim.x) {
+        const uint32_t key = big_list[item];
+        const uint32_t lo = toff[key], nt = toff[key + 1] - lo;
+        const uint32_t lane = threadIdx.x;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t t = lane; t < nt; t += 32) {
+            XYZZ<F> b = partials[lo + t];
+            ec_add(acc, b);
+        }
+        sh[lane] = acc;
+        __syncwarp();
+        for (uint32_t step = 16; step >= 1; step >>= 1) {
+            if (lane < step) {
+                XYZZ<F> b = sh[lane + step];
+                ec_add(acc, b);
+                sh[lane] = acc;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) buckets[key] = acc;
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------- bucket reduction
@@ -382,13 +464,48 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
                                                                  (uint32_t*)d_cursor, (uint32_t*)d_sorted);
         B200ZK_TRY(check_launch(ctx, "msm_scatter"));
     }
+    // task list (buckets cut into <= TASK_LEN entries)
+    void *d_tcount, *d_toff, *d_tasks, *d_partials, *d_big;
+    const uint64_t max_tasks = (uint64_t)n_keys + (max_entries >> LOG_TASK_LEN) + 1;
+    B200ZK_TRY(scratch(ctx, "msm_tcount", ((size_t)n_keys + 1) * 4, &d_tcount));
+    B200ZK_TRY(scratch(ctx, "msm_toff", ((size_t)n_keys + 1) * 4, &d_toff));
+    B200ZK_TRY(scratch(ctx, "msm_tasks", (size_t)max_tasks * 4, &d_tasks));
+    B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)(max_entries >> LOG_TASK_LEN) / FOLD_SMALL_MAX + 8) * 4, &d_big));
+    uint32_t n_tasks = 0;
     {
+        ProfScope ps(ctx, "msm_tasks");
+        msm_task_counts<<<div_up(n_keys, 256), 256, 0, ctx->stream>>>((const uint32_t*)d_offsets, n_keys,
+                                                                      (uint32_t*)d_tcount);
+        B200ZK_TRY(check_launch(ctx, "msm_task_counts"));
+        B200ZK_TRY(exclusive_scan(ctx, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
+        msm_task_list<<<div_up(n_keys, 256), 256, 0, ctx->stream>>>((const uint32_t*)d_toff, n_keys,
+                                                                    (uint32_t*)d_tasks);
+        B200ZK_TRY(check_launch(ctx, "msm_task_list"));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, ctx->stream));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_tasks, (const uint32_t*)d_toff + n_keys, 4, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_partials_g1" : "msm_partials_g2",
+                       ((size_t)n_tasks + 1) * sizeof(XYZZ<F>), &d_partials));
+    uint32_t* big_count = (uint32_t*)d_big;
+    uint32_t* big_list = (uint32_t*)d_big + 1;
+    if (n_tasks) {
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2");
-        msm_accumulate<F><<<div_up(n_keys, 128), 128, 0, ctx->stream>>>((const Affine<F>*)h->d_points,
-                                                                        (const uint32_t*)d_offsets,
-                                                                        (const uint32_t*)d_sorted, n_keys,
-                                                                        (XYZZ<F>*)d_buckets);
+        msm_accumulate<F><<<div_up(n_tasks, 128), 128, 0, ctx->stream>>>(
+            (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
+            (const uint32_t*)d_toff, (const uint32_t*)d_tasks, n_tasks, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
+    }
+    {
+        ProfScope ps(ctx, "msm_fold");
+        msm_fold_small<F><<<div_up(n_keys, 64), 64, 0, ctx->stream>>>((const uint32_t*)d_toff, n_keys,
+                                                                       (const XYZZ<F>*)d_partials, (XYZZ<F>*)d_buckets,
+                                                                       big_list, big_count);
+        B200ZK_TRY(check_launch(ctx, "msm_fold_small"));
+        msm_fold_big<F><<<ctx->sm_count * 4, 32, 0, ctx->stream>>>((const uint32_t*)d_toff, (const XYZZ<F>*)d_partials,
+                                                                   (XYZZ<F>*)d_buckets, big_list, big_count);
+        B200ZK_TRY(check_launch(ctx, "msm_fold_big"));
     }
     // bucket reduction
     const uint32_t sets = (uint32_t)batch * pl.weff;
