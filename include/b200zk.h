@@ -126,6 +126,66 @@ int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scal
                         int scalars_on_device, size_t n, size_t batch, uint8_t* out_affine,
                         uint8_t* out_is_inf);
 
+/* ---- the shielder relation: ConstraintSynthesizer side (host only, no GPU needed) ---------------
+ * R1CS of update_note_circuit (shielder/relations/src/relations/update_note.rs:106-149) with the
+ * concrete Account/Operation of the mock (shielder/mocked_zk/src/account.rs, ops.rs); see
+ * zk-apps_b200/csrc/host_r1cs.hpp.  kind: 0 = deposit, 1 = withdraw.  Variable numbering is
+ * arkworks': z = [1, instance (amount, token, user, new_note_hash, merkle_root, old_nullifier),
+ * witness...].  Matrices come out as CSR, coefficients 32 B Montgomery Fr. */
+typedef struct b200zk_r1cs b200zk_r1cs;
+int b200zk_update_note_r1cs(int kind, uint32_t tree_height, b200zk_r1cs** out);
+void b200zk_r1cs_free(b200zk_r1cs* r);
+int b200zk_r1cs_shape(const b200zk_r1cs* r, uint64_t* num_constraints, uint64_t* num_inputs /* incl. ONE */,
+                      uint64_t* num_aux, uint64_t nnz[3]);
+int b200zk_r1cs_matrix(const b200zk_r1cs* r, int which /*0=A,1=B,2=C*/, uint64_t* row_ptr /* nc+1 */,
+                       uint32_t* cols, uint8_t* vals);
+/* Poseidon parameters of relations/src/lib.rs:17-26 (T=5, R_F=8, R_P=56) generated on the host by
+ * the Grain LFSR: round constants 64*5*32 B, MDS 25*32 B, Montgomery Fr. */
+int b200zk_poseidon_constants(uint8_t* round_constants, uint8_t* mds);
+
+/* ---- K6: batched Poseidon and witness generation ------------------------------------------
+ * b200zk_poseidon_hash_batch: n_hashes independent PoseidonHasher::hash_fix_len_array calls of
+ * `arity` inputs each (halo2-base 0.4.1 semantics [recall]); inputs n_hashes*arity*32 B, out n*32 B.
+ * b200zk_update_note_witness_batch: full R1CS assignment z of each instance.  inputs = batch rows of
+ * (18 + 2*H) Fr in UpdateNoteInput::new argument order (update_note.rs:47-57):
+ *   amount, token, user | new_note_hash | merkle_root | new_note (zk_id, trapdoor, nullifier,
+ *   account_hash) | old_note (same 4) | path_shape[H] (0/1) | path[H] | op_priv.user |
+ *   old_account (token0, balance0, token1, balance1).
+ * out_assignments (host, may be NULL) / d_out_assignments (device, may be NULL): batch*num_vars*32 B.
+ * out_status[b] (may be NULL): 0 = satisfied, 1 = unsatisfied.  Returns B200ZK_ERR_UNSATISFIED if
+ * any instance is unsatisfied (assignments are still written). */
+int b200zk_poseidon_hash_batch(b200zk_ctx* ctx, const uint8_t* inputs, size_t n_hashes, uint32_t arity, uint8_t* out);
+int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
+                                     uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status);
+
+/* ---- Groth16 ------------------------------------------------------------------------------
+ * b200zk_pk_upload: a proving key produced elsewhere (ark_groth16::ProvingKey fields, affine FFI
+ * layout; query lengths: a, b_g1, b_g2 = num_variables, l = num_aux, h = domain_size - 1).
+ * b200zk_groth16_setup: key generation from explicit toxic waste (alpha, beta, gamma, delta, tau:
+ * 5 x 32 B canonical LE) -- ark_groth16::generate_parameters_with_qap [recall]; fixed-base
+ * multiplications run on the GPU.  vk_out (may be NULL): alpha_g1 (96) | beta_g2 (192) |
+ * gamma_g2 (192) | delta_g2 (192) | gamma_abc_g1 (num_inputs * 96).
+ * precompute != 0 stores the window multiples of every query (see b200zk_bases_upload).
+ * b200zk_groth16_prove_batch = create_proof_with_reduction(circuit, pk, r, s) for `batch` full
+ * assignments (batch*num_vars*32 B Montgomery, host or device); r, s: batch*32 B canonical LE.
+ * proofs_out: batch * 192 B = compressed A (48) | B (96) | C (48), ark-serialize / zcash format.
+ * points_out (may be NULL): batch * 384 B = affine A (96) | B (192) | C (96), FFI layout.
+ * b200zk_update_note_prove_batch: witness generation + proving in one call (the user-facing path). */
+int b200zk_pk_upload(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* alpha_g1, const uint8_t* beta_g1,
+                     const uint8_t* beta_g2, const uint8_t* delta_g1, const uint8_t* delta_g2, const uint8_t* a_query,
+                     const uint8_t* b_g1_query, const uint8_t* b_g2_query, const uint8_t* l_query,
+                     const uint8_t* h_query, int precompute, b200zk_pk** out);
+int b200zk_groth16_setup(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t toxic[160], int precompute,
+                         b200zk_pk** out, uint8_t* vk_out);
+void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
+/* which: 0 = a_query, 1 = b_g1_query, 2 = b_g2_query, 3 = l_query, 4 = h_query (first window only) */
+int b200zk_pk_export_query(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint8_t* out, size_t* count);
+int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void* assignments, int on_device,
+                               size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                               uint8_t* points_out);
+int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
+                                   const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,3 +148,31 @@ def verify(pk: ProvingKey, public_inputs, proof) -> bool:
     for x, g in zip(public_inputs, pk.gamma_abc_g1[1:]):
         acc = G1.add(acc, G1.mul(g, x % R))
     return pairing_product_is_one([(G1.neg(A), B), (pk.alpha_g1, pk.beta_g2), (acc, pk.gamma_g2), (Cc, pk.delta_g2)])
+
+
+def proof_via_scalars(matrices, sc: SetupScalars, tox: Toxic, z, r: int, s: int):
+    """The same proof computed in the exponent: every key element is a known multiple of the
+    generator (a_query[i] = a_i G, ...), so A, B, C are single fixed-base multiplications.  An
+    independent, fast derivation used to diff full-size GPU proofs bit for bit."""
+    h = witness_map(matrices, sc.num_inputs, z, sc.n)
+    dot = lambda xs, ys: sum(x * y for x, y in zip(xs, ys)) % R
+    a_s = (tox.alpha + dot(sc.a, z) + r * tox.delta) % R
+    b_s = (tox.beta + dot(sc.b, z) + s * tox.delta) % R
+    c_s = (dot(sc.l, z[sc.num_inputs:]) + dot(sc.h, h[:sc.n - 1]) + s * a_s + r * b_s - r * s % R * tox.delta) % R
+    return G1.mul(G1.gen, a_s), G2.mul(G2.gen, b_s), G1.mul(G1.gen, c_s)
+
+
+def verifying_key_from_toxic(sc: SetupScalars, tox: Toxic):
+    """(alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1) from the toxic waste."""
+    return (G1.mul(G1.gen, tox.alpha), G2.mul(G2.gen, tox.beta), G2.mul(G2.gen, tox.gamma), G2.mul(G2.gen, tox.delta),
+            [G1.mul(G1.gen, k) for k in sc.gamma_abc])
+
+
+def verify_with_vk(vk, public_inputs, proof) -> bool:
+    alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc = vk
+    A, B, Cc = proof
+    if not (G1.on_curve(A) and G2.on_curve(B) and G1.on_curve(Cc)): return False
+    acc = gamma_abc[0]
+    for x, g in zip(public_inputs, gamma_abc[1:]):
+        acc = G1.add(acc, G1.mul(g, x % R))
+    return pairing_product_is_one([(G1.neg(A), B), (alpha_g1, beta_g2), (acc, gamma_g2), (Cc, delta_g2)])

@@ -169,3 +169,10 @@ def synthesize_update_note(w: UpdateNoteWitness, tree_height: int = TREE_HEIGHT)
     assert_equal(cs, matches, LC.const(1))                          # exactly one token matches
     assert_equal(cs, poseidon_hash(cs, new_vec), new_note[3])       # :88-94 (new_note.account_hash)
     return cs
+
+
+def witness_to_inputs(w: UpdateNoteWitness) -> list:
+    """The (18 + 2H) field elements of one instance in UpdateNoteInput::new argument order -- the
+    input row of b200zk_update_note_witness_batch (include/b200zk.h)."""
+    return ([w.amount, w.token, w.user, w.new_note_hash, w.merkle_root] + w.new_note.to_vec() + w.old_note.to_vec()
+            + [1 if s else 0 for s in w.path_shape] + list(w.path) + [w.op_priv_user] + w.old_account.to_vec())

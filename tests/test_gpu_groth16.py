@@ -1,0 +1,147 @@
+"""K6 + Groth16 parity (GPU): batched Poseidon, the update-note witness generator and the full
+prover against the Python oracle, bit-exact, through the C ABI; every proof must also satisfy the
+pairing equation (the stand-in for "the reference verifier accepts")."""
+import numpy as np
+import pytest
+
+import zk_apps_b200 as z
+from oracle.pyref import bls12_381 as bls
+from oracle.pyref import groth16 as og
+from oracle.pyref import poseidon as pos
+from oracle.pyref import relations as rel
+from tests import util
+
+pytestmark = pytest.mark.gpu
+R = bls.R
+TOX = og.Toxic(alpha=0x1111_2222_3333, beta=0x4444_5555_6666_7777, gamma=0x8888_9999, delta=0xaaaa_bbbb_cccc, tau=0xdddd_eeee_ffff_0123)
+
+
+@pytest.mark.parametrize("arity", [1, 2, 3, 4, 5, 8])
+def test_poseidon_hash_batch(ctx, arity):
+    n = 37
+    vals = util.rand_fr(arity, n * arity)
+    vals[:arity] = [0] * arity
+    vals[arity:2 * arity] = [R - 1] * arity
+    out = util.fr_from_mont_array(z.poseidon_hash_batch(ctx, util.fr_mont_array(vals), arity))
+    assert out == [pos.hash_fix_len_array(vals[i * arity:(i + 1) * arity]) for i in range(n)]
+
+
+@pytest.mark.parametrize("kind", [rel.WITHDRAW, rel.DEPOSIT])
+def test_witness_matches_oracle(ctx, kind):
+    relation = z.UpdateNoteRelation(kind, rel.TREE_HEIGHT)
+    ws = [rel.make_witness(10 + i, kind) for i in range(6)]
+    inputs = util.fr_mont_array([v for w in ws for v in rel.witness_to_inputs(w)])
+    out, status = relation.witness_batch(ctx, inputs, len(ws))
+    assert list(status) == [0] * len(ws)
+    nv = relation.num_variables
+    for i, w in enumerate(ws):
+        cs = rel.synthesize_update_note(w)
+        assert cs.is_satisfied() and cs.num_variables == nv
+        assert util.fr_from_mont_array(out[i * nv * 32:(i + 1) * nv * 32]) == cs.z
+
+
+def test_unsatisfied_witness_is_reported(ctx):
+    relation = z.UpdateNoteRelation(rel.WITHDRAW, rel.TREE_HEIGHT)
+    good = rel.make_witness(3, rel.WITHDRAW)
+    rows = []
+    bad_root = rel.witness_to_inputs(good); bad_root[4] = (bad_root[4] + 1) % R          # wrong merkle_root
+    bad_user = rel.witness_to_inputs(good); bad_user[2] = (bad_user[2] + 1) % R          # op_pub.user != op_priv.user
+    overdraw = rel.witness_to_inputs(good); overdraw[0] = (1 << 127)                     # amount > balance -> underflow
+    for r_ in (rel.witness_to_inputs(good), bad_root, bad_user, overdraw):
+        rows += r_
+    out, status = relation.witness_batch(ctx, util.fr_mont_array(rows), 4)
+    assert list(status) == [0, 1, 1, 1]
+    rc = z.lib().b200zk_update_note_witness_batch(ctx.handle, relation.handle, util.fr_mont_array(rows).ctypes.data, 4,
+                                                  None, None, None)
+    assert rc == -6                                                                       # B200ZK_ERR_UNSATISFIED
+
+
+@pytest.fixture(scope="module")
+def withdraw_key(ctx):
+    relation = z.UpdateNoteRelation(rel.WITHDRAW, rel.TREE_HEIGHT)
+    pk = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
+                                                        precompute=True)
+    w0 = rel.make_witness(1, rel.WITHDRAW)
+    cs0 = rel.synthesize_update_note(w0)
+    M = cs0.matrices()
+    sc = og.setup_scalars(M, cs0.num_inputs, cs0.num_variables, TOX)
+    return relation, pk, M, sc
+
+
+def test_setup_matches_oracle(ctx, withdraw_key):
+    """Key generation: vk and sampled query points equal the oracle's scalars times the generator."""
+    relation, pk, M, sc = withdraw_key
+    vk = bytes(pk.vk)
+    assert bls.g1_from_ffi(vk[:96]) == bls.G1.mul(bls.G1_GEN, TOX.alpha)
+    assert bls.g2_from_ffi(vk[96:288]) == bls.G2.mul(bls.G2_GEN, TOX.beta)
+    assert bls.g2_from_ffi(vk[288:480]) == bls.G2.mul(bls.G2_GEN, TOX.gamma)
+    assert bls.g2_from_ffi(vk[480:672]) == bls.G2.mul(bls.G2_GEN, TOX.delta)
+    assert util.g1_list(vk[672:]) == [bls.G1.mul(bls.G1_GEN, k) for k in sc.gamma_abc]
+    for which, scal, grp in ((0, sc.a, 1), (1, sc.b, 1), (2, sc.b, 2), (3, sc.l, 1), (4, sc.h, 1)):
+        q = pk.export_query(which)
+        pts = util.g1_list(q) if grp == 1 else util.g2_list(q)
+        assert len(pts) == len(scal)
+        cv = bls.G1 if grp == 1 else bls.G2
+        for i in (0, 1, 7, len(scal) // 2, len(scal) - 1):
+            assert pts[i] == cv.mul(cv.gen, scal[i]), (which, i)
+
+
+def test_proofs_bit_exact_and_verify(ctx, withdraw_key):
+    """Fixed (r, s): GPU proof bytes == oracle proof bytes; the pairing equation holds; a wrong public
+    input is rejected."""
+    relation, pk, M, sc = withdraw_key
+    ws = [rel.make_witness(40 + i, rel.WITHDRAW) for i in range(3)]
+    zs = [rel.synthesize_update_note(w).z for w in ws]
+    rs = [0x1234567890abcdef + i for i in range(3)]
+    ss = [0xfedcba0987654321 * (i + 1) for i in range(3)]
+    rs[2], ss[2] = 0, 0                                            # degenerate randomness still has to work
+    zbuf = util.fr_mont_array([v for zz in zs for v in zz])
+    proofs, points = z.Groth16.create_proof_with_reduction(pk, zbuf, rs, ss, batch=3, want_points=True)
+    vk = og.verifying_key_from_toxic(sc, TOX)
+    for i, w in enumerate(ws):
+        want = og.proof_via_scalars(M, sc, TOX, zs[i], rs[i], ss[i])
+        pb = bytes(proofs[i * 192:(i + 1) * 192])
+        assert pb == og.proof_to_bytes(want)
+        pt = bytes(points[i * 384:(i + 1) * 384])
+        assert (bls.g1_from_ffi(pt[:96]), bls.g2_from_ffi(pt[96:288]), bls.g1_from_ffi(pt[288:])) == want
+        assert og.proof_from_bytes(pb) == want
+    assert og.verify_with_vk(vk, ws[0].public_inputs(), og.proof_from_bytes(bytes(proofs[:192])))
+    wrong = ws[0].public_inputs(); wrong[0] = (wrong[0] + 1) % R
+    assert not og.verify_with_vk(vk, wrong, og.proof_from_bytes(bytes(proofs[:192])))
+
+
+def test_end_to_end_prove_update_note(ctx, withdraw_key):
+    """The user-facing call: inputs -> witness (K6) -> proof, in one batch; deterministic for fixed r, s."""
+    relation, pk, M, sc = withdraw_key
+    batch = 9
+    ws = [rel.make_witness(70 + i, rel.WITHDRAW) for i in range(batch)]
+    inputs = util.fr_mont_array([v for w in ws for v in rel.witness_to_inputs(w)])
+    rs = util.rand_fr(1, batch); ss = util.rand_fr(2, batch)
+    proofs, status = z.Groth16.prove_update_note(pk, inputs, rs, ss, batch)
+    assert list(status) == [0] * batch
+    proofs2, _ = z.Groth16.prove_update_note(pk, inputs, rs, ss, batch)
+    assert bytes(proofs) == bytes(proofs2)
+    for i in (0, batch - 1):
+        zz = rel.synthesize_update_note(ws[i]).z
+        assert bytes(proofs[i * 192:(i + 1) * 192]) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, zz, rs[i], ss[i]))
+    vk = og.verifying_key_from_toxic(sc, TOX)
+    assert og.verify_with_vk(vk, ws[4].public_inputs(), og.proof_from_bytes(bytes(proofs[4 * 192:5 * 192])))
+    bad = inputs.copy(); bad[4 * 32] ^= 1                          # corrupt merkle_root of instance 0
+    with pytest.raises(z.B200zkError) as e:
+        z.Groth16.prove_update_note(pk, bad, rs, ss, batch)
+    assert e.value.code == -6
+
+
+def test_deposit_relation_proves(ctx):
+    relation = z.UpdateNoteRelation(rel.DEPOSIT, rel.TREE_HEIGHT)
+    pk = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
+                                                        precompute=False)
+    w = rel.make_witness(5, rel.DEPOSIT)
+    cs = rel.synthesize_update_note(w)
+    M = cs.matrices()
+    sc = og.setup_scalars(M, cs.num_inputs, cs.num_variables, TOX)
+    inputs = util.fr_mont_array(rel.witness_to_inputs(w))
+    proofs, status = z.Groth16.prove_update_note(pk, inputs, [77], [99], 1)
+    assert bytes(proofs) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, cs.z, 77, 99))
+    assert og.verify_with_vk(og.verifying_key_from_toxic(sc, TOX), w.public_inputs(), og.proof_from_bytes(bytes(proofs)))
+    pk.free()

@@ -5,4 +5,5 @@ include/b200zk.h (libb200zk.so, built in-tree by build.py).  There is no CPU fal
 fails loudly if the CUDA library is missing, and creating a Context fails without a GPU.
 """
 from .ffi import (B200zkError, Context, lib, lib_path, Radix2EvaluationDomain, VariableBaseMSM,  # noqa: F401
-                  FR_BYTES, G1_BYTES, G2_BYTES, fr_to_mont, fr_from_mont, STATUS)
+                  FR_BYTES, G1_BYTES, G2_BYTES, fr_to_mont, fr_from_mont, STATUS, DEPOSIT, WITHDRAW,
+                  poseidon_constants, poseidon_hash_batch, UpdateNoteRelation, ProvingKey, Groth16)

@@ -1,0 +1,577 @@
+// Groth16 prover pipeline on the GPU (BLS12-381), batched over proofs that share a proving key.
+//
+// Replaces ark_groth16::Groth16::<Bls12_381>::create_proof_with_reduction(circuit, &pk, r, s)
+// with LibsnarkReduction ([recall]; no ark-groth16 pin and no
+// prover of any kind exists in /root/reference -- section 0).  Per batch of B proofs:
+//   1. r1cs_matvec:  a_i = <A_i,z>, b_i = <B_i,z>, c_i = <C_i,z>, a[nc + j] = z[j]  (CSR rows)
+//   2. 3B iNTT -> 3B coset NTT (offset 7) -> h_pointwise (a*b - c) / Z(g)  -> B coset iNTT
+//   3. five batched MSMs over the device-resident queries (a, b_g1, b_g2, l, h), scalars taken
+//      straight from z / h in Montgomery form
+//   4. assembly:  A = alpha + sum a_i z_i + r delta ;  B = beta + sum b_i z_i + s delta  (G1 and G2)
+//                 C = sum l_i aux_i + sum h_i H_i + s A + r B1 - r s delta
+//      and zcash-style compression to 48 + 96 + 48 bytes, all on the device.
+#include <cstring>
+#include <memory>
+
+#include "types.cuh"
+
+using namespace b200zk;
+
+struct Csr {
+    uint32_t* row_ptr = nullptr;
+    uint32_t* cols = nullptr;
+    Fr* vals = nullptr;
+};
+
+struct b200zk_pk {
+    uint32_t num_constraints = 0, num_inputs = 0, num_aux = 0, log_n = 0;
+    int kind = 0;
+    uint32_t tree_height = 0;
+    Csr m[3];
+    b200zk_bases a_query, b_g1_query, b_g2_query, l_query, h_query;
+    G1Affine alpha_g1, beta_g1, delta_g1;
+    G2Affine beta_g2, delta_g2;
+    void* d_singles = nullptr;  // alpha_g1, beta_g1, delta_g1 (G1Affine x3) then beta_g2, delta_g2 (G2Affine x2)
+};
+
+namespace {
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// abc layout: [3][batch][n]
+__global__ void r1cs_matvec(Csr A, Csr B, Csr C, uint32_t nc, uint32_t num_inputs, uint32_t num_vars, uint32_t log_n,
+                            const Fr* __restrict__ z_all, uint32_t batch, Fr* __restrict__ abc) {
+    const uint32_t n = 1u << log_n;
+    const uint32_t rows = nc + num_inputs;
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)rows * batch) return;
+    const uint32_t b = (uint32_t)(t / rows), i = (uint32_t)(t % rows);
+    const Fr* z = z_all + (size_t)b * num_vars;
+    if (i >= nc) {  // input-consistency rows: a[nc + j] = z[j]
+        st_fr(abc + ((size_t)0 * batch + b) * n + i, ld_fr(z + (i - nc)));
+        return;
+    }
+    const Csr* M[3] = {&A, &B, &C};
+#pragma unroll 1
+    for (int m = 0; m < 3; m++) {
+        Fr acc = Fr::zero();
+        const uint32_t lo = M[m]->row_ptr[i], hi = M[m]->row_ptr[i + 1];
+        for (uint32_t k = lo; k < hi; k++) acc = fp_add(acc, fp_mul(ld_fr(M[m]->vals + k), ld_fr(z + M[m]->cols[k])));
+        st_fr(abc + ((size_t)m * batch + b) * n + i, acc);
+    }
+}
+
+// a <- (a*b - c) * zinv over batch*n elements
+__global__ void h_pointwise(Fr* __restrict__ abc, size_t count, Fr zinv) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    Fr a = ld_fr(abc + t), b = ld_fr(abc + count + t), c = ld_fr(abc + 2 * count + t);
+    st_fr(abc + t, fp_mul(fp_sub(fp_mul(a, b), c), zinv));
+}
+
+struct Singles {
+    G1Affine alpha_g1, beta_g1, delta_g1;
+    G2Affine beta_g2, delta_g2;
+};
+
+__device__ __forceinline__ void load_k(const uint8_t* p, uint32_t* k) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) k[i] = q[i];
+}
+
+// phase 1: t = j * batch + b ; j = 0: r*delta1, 1: s*delta1, 2: s*delta2
+__global__ void __launch_bounds__(32) finalize_phase1(const Singles* __restrict__ sg, const uint8_t* __restrict__ r,
+                                                      const uint8_t* __restrict__ s, uint32_t batch,
+                                                      G1XYZZ* __restrict__ t_g1 /*[2][batch]*/,
+                                                      G2XYZZ* __restrict__ t_g2 /*[batch]*/) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * batch) return;
+    const uint32_t j = t / batch, b = t % batch;
+    uint32_t k[8];
+    load_k((j == 0 ? r : s) + (size_t)b * 32, k);
+    if (j < 2) t_g1[(size_t)j * batch + b] = ec_mul_scalar(G1XYZZ::from_affine(sg->delta_g1), k);
+    else t_g2[b] = ec_mul_scalar(G2XYZZ::from_affine(sg->delta_g2), k);
+}
+
+// msm_g1 layout: [4][batch] = a, b_g1, l, h ; phase 2: j = 0: s*A, 1: r*B1, 2: (r*s)*delta1
+__global__ void __launch_bounds__(32) finalize_phase2(const Singles* __restrict__ sg, const uint8_t* __restrict__ r,
+                                                      const uint8_t* __restrict__ s, uint32_t batch,
+                                                      const G1Affine* __restrict__ msm_g1,
+                                                      const G1XYZZ* __restrict__ t_g1, G1XYZZ* __restrict__ u_g1 /*[3][batch]*/) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * batch) return;
+    const uint32_t j = t / batch, b = t % batch;
+    uint32_t kr[8], ks[8];
+    load_k(r + (size_t)b * 32, kr);
+    load_k(s + (size_t)b * 32, ks);
+    G1XYZZ res;
+    if (j == 0) {  // s * A,  A = alpha + msm_a + r*delta1
+        G1XYZZ A = t_g1[b];
+        ec_madd(A, sg->alpha_g1);
+        ec_madd(A, msm_g1[(size_t)0 * batch + b]);
+        res = ec_mul_scalar(A, ks);
+    } else if (j == 1) {  // r * B1,  B1 = beta1 + msm_b1 + s*delta1
+        G1XYZZ B1 = t_g1[(size_t)batch + b];
+        ec_madd(B1, sg->beta_g1);
+        ec_madd(B1, msm_g1[(size_t)1 * batch + b]);
+        res = ec_mul_scalar(B1, kr);
+    } else {  // (r*s mod r) * delta1
+        Fr fr_r, fr_s;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            fr_r.v[i] = kr[i];
+            fr_s.v[i] = ks[i];
+        }
+        Fr rs = fp_from_mont(fp_mul(fp_to_mont(fr_r), fp_to_mont(fr_s)));
+        res = ec_mul_scalar(G1XYZZ::from_affine(sg->delta_g1), rs.v);
+    }
+    u_g1[(size_t)j * batch + b] = res;
+}
+
+// canonical big-endian bytes of an Fq (48 B)
+__device__ __forceinline__ void fq_to_be(const Fq& mont, uint8_t* out) {
+    Fq c = fp_from_mont(mont);
+    for (int k = 0; k < 48; k++) {
+        int byte = 47 - k;
+        out[k] = (uint8_t)(c.v[byte >> 2] >> (8 * (byte & 3)));
+    }
+}
+// y > (p-1)/2  <=>  2y >= p  (canonical y)
+__device__ __forceinline__ bool fq_lex_largest(const Fq& mont) {
+    Fq c = fp_from_mont(mont);
+    uint32_t d[13];
+    uint32_t carry = 0;
+    for (int i = 0; i < 12; i++) {
+        d[i] = (c.v[i] << 1) | carry;
+        carry = c.v[i] >> 31;
+    }
+    d[12] = carry;
+    if (d[12]) return true;
+    for (int i = 11; i >= 0; i--) {
+        if (d[i] > FqCfg::mod(i)) return true;
+        if (d[i] < FqCfg::mod(i)) return false;
+    }
+    return true;  // 2y == p cannot happen (p odd)
+}
+__device__ void compress_g1(const G1Affine& p, uint8_t* out) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 48; i++) out[i] = 0;
+        out[0] = 0xC0;
+        return;
+    }
+    fq_to_be(p.x, out);
+    out[0] |= 0x80 | (fq_lex_largest(p.y) ? 0x20 : 0);
+}
+__device__ void compress_g2(const G2Affine& p, uint8_t* out) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 96; i++) out[i] = 0;
+        out[0] = 0xC0;
+        return;
+    }
+    fq_to_be(p.x.c1, out);
+    fq_to_be(p.x.c0, out + 48);
+    const bool largest = p.y.c1.is_zero() ? fq_lex_largest(p.y.c0) : fq_lex_largest(p.y.c1);
+    out[0] |= 0x80 | (largest ? 0x20 : 0);
+}
+
+// phase 3: t = j * batch + b ; j = 0: A, 1: B (G2), 2: C -> affine + compressed bytes
+__global__ void __launch_bounds__(32) finalize_phase3(const Singles* __restrict__ sg, uint32_t batch,
+                                                      const G1Affine* __restrict__ msm_g1,
+                                                      const G2Affine* __restrict__ msm_g2,
+                                                      const G1XYZZ* __restrict__ t_g1, const G2XYZZ* __restrict__ t_g2,
+                                                      const G1XYZZ* __restrict__ u_g1, uint8_t* __restrict__ proofs,
+                                                      uint8_t* __restrict__ points /* may be null: 384 B per proof */) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * batch) return;
+    const uint32_t j = t / batch, b = t % batch;
+    uint8_t* out = proofs + (size_t)b * 192;
+    if (j == 0) {
+        G1XYZZ A = t_g1[b];
+        ec_madd(A, sg->alpha_g1);
+        ec_madd(A, msm_g1[(size_t)0 * batch + b]);
+        G1Affine a = ec_to_affine(A);
+        compress_g1(a, out);
+        if (points) memcpy(points + (size_t)b * 384, &a, 96);
+    } else if (j == 1) {
+        G2XYZZ B = t_g2[b];
+        ec_madd(B, sg->beta_g2);
+        ec_madd(B, msm_g2[b]);
+        G2Affine a = ec_to_affine(B);
+        compress_g2(a, out + 48);
+        if (points) memcpy(points + (size_t)b * 384 + 96, &a, 192);
+    } else {
+        G1XYZZ Cc = u_g1[(size_t)0 * batch + b];  // s*A
+        G1XYZZ x = u_g1[(size_t)1 * batch + b];   // r*B1
+        ec_add(Cc, x);
+        x = ec_neg(u_g1[(size_t)2 * batch + b]);  // - r*s*delta1
+        ec_add(Cc, x);
+        ec_madd(Cc, msm_g1[(size_t)2 * batch + b]);  // l
+        ec_madd(Cc, msm_g1[(size_t)3 * batch + b]);  // h
+        G1Affine a = ec_to_affine(Cc);
+        compress_g1(a, out + 144);
+        if (points) memcpy(points + (size_t)b * 384 + 288, &a, 96);
+    }
+}
+
+int upload_csr(b200zk_ctx* ctx, const std::vector<host::LC>& M, Csr* out) {
+    std::vector<uint32_t> rp(M.size() + 1), cols;
+    std::vector<Fr> vals;
+    for (size_t i = 0; i < M.size(); i++) {
+        rp[i] = (uint32_t)cols.size();
+        for (auto& e : M[i].t) {
+            cols.push_back(e.first);
+            vals.push_back(e.second);
+        }
+    }
+    rp[M.size()] = (uint32_t)cols.size();
+    B200ZK_CUDA(ctx, cudaMalloc(&out->row_ptr, rp.size() * 4));
+    B200ZK_CUDA(ctx, cudaMalloc(&out->cols, std::max<size_t>(1, cols.size()) * 4));
+    B200ZK_CUDA(ctx, cudaMalloc(&out->vals, std::max<size_t>(1, vals.size()) * sizeof(Fr)));
+    B200ZK_CUDA(ctx, cudaMemcpy(out->row_ptr, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice));
+    B200ZK_CUDA(ctx, cudaMemcpy(out->cols, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice));
+    B200ZK_CUDA(ctx, cudaMemcpy(out->vals, vals.data(), vals.size() * sizeof(Fr), cudaMemcpyHostToDevice));
+    return B200ZK_OK;
+}
+
+void free_pk(b200zk_pk* pk) {
+    for (auto& m : pk->m) {
+        if (m.row_ptr) cudaFree(m.row_ptr);
+        if (m.cols) cudaFree(m.cols);
+        if (m.vals) cudaFree(m.vals);
+    }
+    for (b200zk_bases* h : {&pk->a_query, &pk->b_g1_query, &pk->b_g2_query, &pk->l_query, &pk->h_query})
+        if (h->d_points) cudaFree(h->d_points);
+    if (pk->d_singles) cudaFree(pk->d_singles);
+    delete pk;
+}
+
+int pk_common(b200zk_ctx* ctx, const b200zk_r1cs* r, b200zk_pk* pk) {
+    const host::R1CS& cs = r->cs;
+    pk->num_constraints = (uint32_t)cs.A.size();
+    pk->num_inputs = cs.num_inputs;
+    pk->num_aux = cs.num_aux;
+    pk->kind = cs.kind;
+    pk->tree_height = cs.tree_height;
+    uint32_t lg = 0;
+    while ((1ull << lg) < (uint64_t)pk->num_constraints + pk->num_inputs) lg++;
+    pk->log_n = lg;
+    B200ZK_TRY(upload_csr(ctx, cs.A, &pk->m[0]));
+    B200ZK_TRY(upload_csr(ctx, cs.B, &pk->m[1]));
+    B200ZK_TRY(upload_csr(ctx, cs.C, &pk->m[2]));
+    return B200ZK_OK;
+}
+
+int pk_singles(b200zk_ctx* ctx, b200zk_pk* pk) {
+    Singles sg{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
+    B200ZK_CUDA(ctx, cudaMalloc(&pk->d_singles, sizeof(Singles)));
+    B200ZK_CUDA(ctx, cudaMemcpy(pk->d_singles, &sg, sizeof(sg), cudaMemcpyHostToDevice));
+    return B200ZK_OK;
+}
+
+Fr fr_from_le(const uint8_t* p) {  // canonical LE -> Montgomery (host)
+    Fr c;
+    memcpy(&c, p, 32);
+    return fp_to_mont(c);
+}
+
+}  // namespace
+
+namespace b200zk {
+
+// d_z: batch * num_vars Fr (Montgomery).  r, s: batch * 32 B canonical, host.
+int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, const uint8_t* r,
+                         const uint8_t* s, uint8_t* proofs_out, uint8_t* points_out) {
+    const uint32_t n = 1u << pk->log_n, nv = pk->num_inputs + pk->num_aux;
+    const size_t B = batch;
+    void *d_abc, *d_rs, *d_msm1, *d_msm2, *d_t1, *d_t2, *d_u1, *d_proofs, *d_points = nullptr;
+    B200ZK_TRY(scratch(ctx, "g16_abc", 3 * B * n * sizeof(Fr), &d_abc));
+    B200ZK_TRY(scratch(ctx, "g16_rs", 2 * B * 32, &d_rs));
+    B200ZK_TRY(scratch(ctx, "g16_msm1", 4 * B * sizeof(G1Affine), &d_msm1));
+    B200ZK_TRY(scratch(ctx, "g16_msm2", B * sizeof(G2Affine), &d_msm2));
+    B200ZK_TRY(scratch(ctx, "g16_t1", 2 * B * sizeof(G1XYZZ), &d_t1));
+    B200ZK_TRY(scratch(ctx, "g16_t2", B * sizeof(G2XYZZ), &d_t2));
+    B200ZK_TRY(scratch(ctx, "g16_u1", 3 * B * sizeof(G1XYZZ), &d_u1));
+    B200ZK_TRY(scratch(ctx, "g16_proofs", B * 192, &d_proofs));
+    if (points_out) B200ZK_TRY(scratch(ctx, "g16_points", B * 384, &d_points));
+    uint8_t* d_r = (uint8_t*)d_rs;
+    uint8_t* d_s = d_r + B * 32;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_r, r, B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_s, s, B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const Singles* sg = (const Singles*)pk->d_singles;
+    // scalar multiples of delta do not depend on the witness: issue them first
+    finalize_phase1<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, d_r, d_s, (uint32_t)B, (G1XYZZ*)d_t1, (G2XYZZ*)d_t2);
+    B200ZK_TRY(check_launch(ctx, "finalize_phase1"));
+
+    // ---- H(x) = (A*B - C) / Z
+    Fr* abc = (Fr*)d_abc;
+    B200ZK_CUDA(ctx, cudaMemsetAsync(d_abc, 0, 3 * B * n * sizeof(Fr), ctx->stream));
+    {
+        ProfScope ps(ctx, "r1cs_matvec");
+        const size_t threads = (size_t)(pk->num_constraints + pk->num_inputs) * B;
+        r1cs_matvec<<<div_up(threads, 128), 128, 0, ctx->stream>>>(pk->m[0], pk->m[1], pk->m[2], pk->num_constraints,
+                                                                   pk->num_inputs, nv, pk->log_n, d_z, (uint32_t)B, abc);
+        B200ZK_TRY(check_launch(ctx, "r1cs_matvec"));
+    }
+    const Fr g = host::fr_from_u64(7);  // Fr::GENERATOR, the coset offset arkworks' Groth16 uses
+    B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, true, nullptr, 3 * B));
+    B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, false, &g, 3 * B));
+    {
+        // Z(g) = g^n - 1 on the coset
+        Fr gn = g;
+        for (uint32_t i = 0; i < pk->log_n; i++) gn = fp_sqr(gn);
+        const Fr zinv = fp_inv(fp_sub(gn, Fr::one()));
+        ProfScope ps(ctx, "h_pointwise");
+        h_pointwise<<<div_up(B * n, 256), 256, 0, ctx->stream>>>(abc, B * n, zinv);
+        B200ZK_TRY(check_launch(ctx, "h_pointwise"));
+    }
+    B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, true, &g, B));
+
+    // ---- MSMs (scalars in Montgomery form straight from z / h)
+    G1Affine* m1 = (G1Affine*)d_msm1;
+    const uint32_t* zs = (const uint32_t*)d_z;
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->a_query, zs, nv, nv, B, true, m1 + 0 * B));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->b_g1_query, zs, nv, nv, B, true, m1 + 1 * B));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->l_query, zs + (size_t)pk->num_inputs * 8, pk->num_aux, nv, B, true, m1 + 2 * B));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B));
+    B200ZK_TRY(msm_device<Fq2>(ctx, &pk->b_g2_query, zs, nv, nv, B, true, (G2Affine*)d_msm2));
+
+    // ---- assembly + compression
+    {
+        ProfScope ps(ctx, "finalize");
+        finalize_phase2<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, d_r, d_s, (uint32_t)B, m1, (const G1XYZZ*)d_t1,
+                                                                   (G1XYZZ*)d_u1);
+        B200ZK_TRY(check_launch(ctx, "finalize_phase2"));
+        finalize_phase3<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, (uint32_t)B, m1, (const G2Affine*)d_msm2,
+                                                                   (const G1XYZZ*)d_t1, (const G2XYZZ*)d_t2,
+                                                                   (const G1XYZZ*)d_u1, (uint8_t*)d_proofs,
+                                                                   (uint8_t*)d_points);
+        B200ZK_TRY(check_launch(ctx, "finalize_phase3"));
+    }
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(proofs_out, d_proofs, B * 192, cudaMemcpyDeviceToHost, ctx->stream));
+    if (points_out) B200ZK_CUDA(ctx, cudaMemcpyAsync(points_out, d_points, B * 384, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk
+
+extern "C" {
+
+int b200zk_groth16_setup(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t toxic[160], int precompute,
+                         b200zk_pk** out, uint8_t* vk_out) {
+    if (!ctx || !r || !toxic || !out) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const host::R1CS& cs = r->cs;
+    std::unique_ptr<b200zk_pk, void (*)(b200zk_pk*)> pk(new b200zk_pk(), free_pk);
+    B200ZK_TRY(pk_common(ctx, r, pk.get()));
+    const uint32_t nc = pk->num_constraints, ni = pk->num_inputs, nv = ni + pk->num_aux, n = 1u << pk->log_n;
+    const Fr alpha = fr_from_le(toxic), beta = fr_from_le(toxic + 32), gamma = fr_from_le(toxic + 64),
+             delta = fr_from_le(toxic + 96), tau = fr_from_le(toxic + 128);
+    if (gamma.is_zero() || delta.is_zero()) return fail(ctx, B200ZK_ERR_BAD_ARG, "gamma/delta must be non-zero");
+    // ---- QAP at tau: Lagrange coefficients u_i = Z(tau) w^i / (n (tau - w^i))   (batch inversion)
+    Fr w = Fr{{0x5f0e466au, 0xb9b58d8cu, 0x1819d7ecu, 0x5b1b4c80u, 0x52a31e64u, 0x0af53ae3u, 0x19e9b27bu, 0x5bf3addau}};
+    for (uint32_t i = pk->log_n; i < 32; i++) w = fp_sqr(w);
+    Fr tn = tau;
+    for (uint32_t i = 0; i < pk->log_n; i++) tn = fp_sqr(tn);
+    const Fr zt = fp_sub(tn, Fr::one());
+    if (zt.is_zero()) return fail(ctx, B200ZK_ERR_BAD_ARG, "tau lies in the evaluation domain");
+    std::vector<Fr> wi(n), den(n), pref(n), u(n);
+    Fr cur = Fr::one();
+    for (uint32_t i = 0; i < n; i++) {
+        wi[i] = cur;
+        den[i] = fp_sub(tau, cur);
+        cur = fp_mul(cur, w);
+    }
+    Fr run = Fr::one();
+    for (uint32_t i = 0; i < n; i++) {
+        pref[i] = run;
+        run = fp_mul(run, den[i]);
+    }
+    Fr inv_all = fp_inv(run);
+    const Fr scale = fp_mul(zt, fp_inv(host::fr_from_u64(n)));
+    for (int i = (int)n - 1; i >= 0; i--) {
+        Fr inv_i = fp_mul(inv_all, pref[i]);
+        inv_all = fp_mul(inv_all, den[i]);
+        u[i] = fp_mul(fp_mul(scale, wi[i]), inv_i);
+    }
+    std::vector<Fr> a(nv, Fr::zero()), b(nv, Fr::zero()), c(nv, Fr::zero());
+    for (uint32_t i = 0; i < ni; i++) a[i] = u[nc + i];
+    for (uint32_t i = 0; i < nc; i++) {
+        for (auto& e : cs.A[i].t) a[e.first] = fp_add(a[e.first], fp_mul(u[i], e.second));
+        for (auto& e : cs.B[i].t) b[e.first] = fp_add(b[e.first], fp_mul(u[i], e.second));
+        for (auto& e : cs.C[i].t) c[e.first] = fp_add(c[e.first], fp_mul(u[i], e.second));
+    }
+    const Fr ginv = fp_inv(gamma), dinv = fp_inv(delta);
+    // scalar list (canonical): [alpha, beta, delta | gamma_abc (ni) | a (nv) | b (nv) | l (num_aux) | h (n-1)]
+    std::vector<Fr> sc;
+    sc.reserve(3 + ni + 2 * nv + pk->num_aux + n);
+    sc.push_back(alpha);
+    sc.push_back(beta);
+    sc.push_back(delta);
+    for (uint32_t i = 0; i < nv; i++) {
+        Fr comb = fp_add(fp_add(fp_mul(beta, a[i]), fp_mul(alpha, b[i])), c[i]);
+        if (i < ni) sc.push_back(fp_mul(comb, ginv));
+    }
+    for (auto& x : a) sc.push_back(x);
+    for (auto& x : b) sc.push_back(x);
+    for (uint32_t i = ni; i < nv; i++) {
+        Fr comb = fp_add(fp_add(fp_mul(beta, a[i]), fp_mul(alpha, b[i])), c[i]);
+        sc.push_back(fp_mul(comb, dinv));
+    }
+    Fr ti = fp_mul(zt, dinv);
+    for (uint32_t i = 0; i + 1 < n; i++) {
+        sc.push_back(ti);
+        ti = fp_mul(ti, tau);
+    }
+    for (auto& x : sc) x = fp_from_mont(x);
+    std::vector<Fr> sc2 = {fp_from_mont(beta), fp_from_mont(gamma), fp_from_mont(delta)};
+    sc2.insert(sc2.end(), sc.begin() + 3 + ni + nv, sc.begin() + 3 + ni + 2 * nv);  // b (already canonical)
+
+    void *ds1, *ds2, *dp1, *dp2;
+    B200ZK_TRY(scratch(ctx, "setup_s1", sc.size() * 32, &ds1));
+    B200ZK_TRY(scratch(ctx, "setup_s2", sc2.size() * 32, &ds2));
+    B200ZK_TRY(scratch(ctx, "setup_p1", sc.size() * sizeof(G1Affine), &dp1));
+    B200ZK_TRY(scratch(ctx, "setup_p2", sc2.size() * sizeof(G2Affine), &dp2));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ds1, sc.data(), sc.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(ds2, sc2.data(), sc2.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(b200zk_fixed_base_mul_device(ctx, 1, ds1, sc.size(), dp1));
+    B200ZK_TRY(b200zk_fixed_base_mul_device(ctx, 2, ds2, sc2.size(), dp2));
+    const G1Affine* p1 = (const G1Affine*)dp1;
+    const G2Affine* p2 = (const G2Affine*)dp2;
+    G1Affine s1[3];
+    G2Affine s2[3];
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s1, p1, sizeof(s1), cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(s2, p2, sizeof(s2), cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    pk->alpha_g1 = s1[0];
+    pk->beta_g1 = s1[1];
+    pk->delta_g1 = s1[2];
+    pk->beta_g2 = s2[0];
+    pk->delta_g2 = s2[2];
+    if (vk_out) {  // alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | gamma_abc_g1[ni]
+        memcpy(vk_out, &s1[0], 96);
+        memcpy(vk_out + 96, &s2[0], 192);
+        memcpy(vk_out + 288, &s2[1], 192);
+        memcpy(vk_out + 480, &s2[2], 192);
+        B200ZK_CUDA(ctx, cudaMemcpy(vk_out + 672, p1 + 3, (size_t)ni * 96, cudaMemcpyDeviceToHost));
+    }
+    pk->a_query.group = pk->b_g1_query.group = pk->l_query.group = pk->h_query.group = 1;
+    pk->b_g2_query.group = 2;
+    size_t off = 3 + ni;
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->a_query, p1 + off, true, nullptr, nv, precompute));
+    off += nv;
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->b_g1_query, p1 + off, true, nullptr, nv, precompute));
+    off += nv;
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->l_query, p1 + off, true, nullptr, pk->num_aux, precompute));
+    off += pk->num_aux;
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->h_query, p1 + off, true, nullptr, n - 1, precompute));
+    B200ZK_TRY(bases_build<Fq2>(ctx, &pk->b_g2_query, p2 + 3, true, nullptr, nv, precompute));
+    B200ZK_TRY(pk_singles(ctx, pk.get()));
+    *out = pk.release();
+    return B200ZK_OK;
+}
+
+int b200zk_pk_upload(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* alpha_g1, const uint8_t* beta_g1,
+                     const uint8_t* beta_g2, const uint8_t* delta_g1, const uint8_t* delta_g2, const uint8_t* a_query,
+                     const uint8_t* b_g1_query, const uint8_t* b_g2_query, const uint8_t* l_query,
+                     const uint8_t* h_query, int precompute, b200zk_pk** out) {
+    if (!ctx || !r || !out || !alpha_g1 || !beta_g1 || !beta_g2 || !delta_g1 || !delta_g2 || !a_query || !b_g1_query ||
+        !b_g2_query || !l_query || !h_query)
+        return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<b200zk_pk, void (*)(b200zk_pk*)> pk(new b200zk_pk(), free_pk);
+    B200ZK_TRY(pk_common(ctx, r, pk.get()));
+    const uint32_t nv = pk->num_inputs + pk->num_aux, n = 1u << pk->log_n;
+    memcpy(&pk->alpha_g1, alpha_g1, 96);
+    memcpy(&pk->beta_g1, beta_g1, 96);
+    memcpy(&pk->delta_g1, delta_g1, 96);
+    memcpy(&pk->beta_g2, beta_g2, 192);
+    memcpy(&pk->delta_g2, delta_g2, 192);
+    pk->a_query.group = pk->b_g1_query.group = pk->l_query.group = pk->h_query.group = 1;
+    pk->b_g2_query.group = 2;
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->a_query, (const G1Affine*)a_query, false, nullptr, nv, precompute));
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->b_g1_query, (const G1Affine*)b_g1_query, false, nullptr, nv, precompute));
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->l_query, (const G1Affine*)l_query, false, nullptr, pk->num_aux, precompute));
+    B200ZK_TRY(bases_build<Fq>(ctx, &pk->h_query, (const G1Affine*)h_query, false, nullptr, n - 1, precompute));
+    B200ZK_TRY(bases_build<Fq2>(ctx, &pk->b_g2_query, (const G2Affine*)b_g2_query, false, nullptr, nv, precompute));
+    B200ZK_TRY(pk_singles(ctx, pk.get()));
+    *out = pk.release();
+    return B200ZK_OK;
+}
+
+void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
+    if (!pk) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    free_pk(pk);
+}
+
+int b200zk_pk_export_query(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint8_t* out, size_t* count) {
+    if (!ctx || !pk || which < 0 || which > 4) return B200ZK_ERR_BAD_ARG;
+    const b200zk_bases* h = which == 0 ? &pk->a_query : which == 1 ? &pk->b_g1_query : which == 2 ? &pk->b_g2_query
+                            : which == 3 ? &pk->l_query : &pk->h_query;
+    if (count) *count = h->n;
+    if (out) B200ZK_CUDA(ctx, cudaMemcpy(out, h->d_points, h->n * (h->group == 1 ? 96 : 192), cudaMemcpyDeviceToHost));
+    return B200ZK_OK;
+}
+
+int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void* assignments, int on_device,
+                               size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                               uint8_t* points_out) {
+    if (!ctx || !pk || !assignments || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nv = pk->num_inputs + pk->num_aux;
+    const Fr* dz = (const Fr*)assignments;
+    if (!on_device) {
+        void* d;
+        B200ZK_TRY(scratch(ctx, "g16_z", batch * nv * sizeof(Fr), &d));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(d, assignments, batch * nv * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+        dz = (const Fr*)d;
+    }
+    return groth16_prove_device(ctx, pk, dz, batch, r, s, proofs_out, points_out);
+}
+
+int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
+                                   const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {
+    if (!ctx || !pk || !inputs || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t H = pk->tree_height, nv = pk->num_inputs + pk->num_aux;
+    const size_t in_bytes = batch * (18 + 2 * (size_t)H) * 32;
+    void *din, *dz, *dst;
+    B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
+    B200ZK_TRY(scratch(ctx, "g16_z", batch * (size_t)nv * sizeof(Fr), &dz));
+    B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(update_note_witness_device(ctx, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
+    std::vector<uint32_t> st(batch);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool bad = false;
+    for (size_t i = 0; i < batch; i++) {
+        if (out_status) out_status[i] = (uint8_t)st[i];
+        if (st[i] & 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "witness layout does not match the R1CS (internal error)");
+        bad = bad || (st[i] & 1);
+    }
+    // like arkworks, an unsatisfied instance is an error, not a proof (SynthesisError::Unsatisfiable in debug builds)
+    if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the update-note relation");
+    return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, r, s, proofs_out, nullptr);
+}
+
+}  // extern "C"

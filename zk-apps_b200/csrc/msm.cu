@@ -23,18 +23,9 @@
 #include <algorithm>
 #include <cstring>
 
-#include "common.cuh"
-#include "ec.cuh"
+#include "types.cuh"
 
 using namespace b200zk;
-
-struct b200zk_bases {
-    int group = 0;           // 1 = G1, 2 = G2
-    size_t n = 0;            // points per window
-    void* d_points = nullptr;  // Affine<F>[n * (precomputed ? windows : 1)]
-    int precomputed = 0;
-    uint32_t c = 0, windows = 0;
-};
 
 namespace {
 
@@ -573,6 +564,9 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host source buffers may go away
     return B200ZK_OK;
 }
+
+template int bases_build<Fq>(b200zk_ctx*, b200zk_bases*, const Affine<Fq>*, bool, const uint8_t*, size_t, int);
+template int bases_build<Fq2>(b200zk_ctx*, b200zk_bases*, const Affine<Fq2>*, bool, const uint8_t*, size_t, int);
 
 }  // namespace b200zk
 

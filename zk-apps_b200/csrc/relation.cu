@@ -1,0 +1,367 @@
+// K6 -- batched Poseidon (t=5, alpha=5, R_F=8, R_P=56) and the shielder "update note" witness
+// generator, plus the host-side R1CS export of the same relation.
+//
+// Spec: /root/reference/shielder/relations/src/relations/update_note.rs:106-149 (statement),
+// merkle_proof.rs:38-61 (path walk), lib.rs:17-26 (Poseidon parameters); the permutation itself
+// lives in the un-vendored halo2-base 0.4.1 (PARITY UNPINNED, see oracle/pyref/poseidon.py).
+//
+// Mapping: one proof per 8-lane group (4 proofs per warp).  Lanes 0..4 of a group each hold one
+// word of the Poseidon state; the 5x5 MDS row products exchange state words with warp shuffles.
+// Every S-box writes its (x^2, x^4, x^5) straight into the proof's assignment vector z, in the
+// order host_r1cs.hpp allocates them, so the R1CS witness is a by-product of hashing.
+#include <cstring>
+#include <memory>
+
+#include "types.cuh"
+
+using namespace b200zk;
+using b200zk::host::PoseidonConsts;
+
+namespace {
+
+constexpr int GROUP = 8;  // lanes per proof
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    Fr r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+// word `src` (0..7) of this lane's group
+__device__ __forceinline__ Fr group_bcast(const Fr& v, int src) {
+    const int lane = threadIdx.x & 31;
+    const int from = (lane & ~(GROUP - 1)) + src;
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], from);
+    return r;
+}
+
+// Cooperative permutation: lane l (< 5) holds state word l.  trace (may be null) receives the
+// 96 * 3 S-box witnesses.  All 32 lanes of the warp must call this together.
+__device__ void poseidon_permute(Fr& s, int l, const PoseidonConsts* pc, Fr* trace) {
+    const int half = host::POSEIDON_RF / 2;
+    int sbox = 0;
+    for (int rnd = 0; rnd < host::POSEIDON_ROUNDS; rnd++) {
+        const bool full = rnd < half || rnd >= half + host::POSEIDON_RP;
+        if (l < host::POSEIDON_T) {
+            s = fp_add(s, ld_fr(&pc->rc[rnd][l]));
+            if (full || l == 0) {
+                Fr x2 = fp_sqr(s);
+                Fr x4 = fp_sqr(x2);
+                Fr x5 = fp_mul(x4, s);
+                if (trace) {
+                    Fr* t = trace + (size_t)(sbox + (full ? l : 0)) * 3;
+                    st_fr(t, x2);
+                    st_fr(t + 1, x4);
+                    st_fr(t + 2, x5);
+                }
+                s = x5;
+            }
+        }
+        sbox += full ? host::POSEIDON_T : 1;
+        Fr acc = Fr::zero();
+#pragma unroll 1
+        for (int j = 0; j < host::POSEIDON_T; j++) {
+            Fr sj = group_bcast(s, j);
+            if (l < host::POSEIDON_T) acc = fp_add(acc, fp_mul(ld_fr(&pc->mds[l][j]), sj));
+        }
+        s = acc;
+    }
+}
+
+// hash_fix_len_array of `n_in` inputs (n_in in {2, 4} here, any n works): lane l in 1..4 supplies
+// input (chunk*4 + l - 1) through `in_of(lane_input_index)`.  Returns the digest in every lane.
+template <class GetIn>
+__device__ Fr poseidon_hash(int n_in, GetIn in_of, int l, const PoseidonConsts* pc, Fr* trace) {
+    Fr s = Fr::zero();
+    if (l == 0) s = ld_fr(&pc->two64);
+    const int chunks = n_in / host::POSEIDON_RATE + 1;
+    for (int c = 0; c < chunks; c++) {
+        const int lo = c * host::POSEIDON_RATE;
+        const int len = lo < n_in ? min(host::POSEIDON_RATE, n_in - lo) : 0;
+        if (l >= 1 && l <= len) s = fp_add(s, in_of(lo + l - 1));
+        if (len + 1 < host::POSEIDON_T && l == len + 1) s = fp_add(s, Fr::one());
+        poseidon_permute(s, l, pc, trace ? trace + (size_t)c * host::POSEIDON_TRACE : nullptr);
+    }
+    return group_bcast(s, 1);
+}
+
+__device__ __forceinline__ bool fits_bits128(const Fr& canon) {
+    return (canon.v[4] | canon.v[5] | canon.v[6] | canon.v[7]) == 0;
+}
+
+// inputs per proof, each a Montgomery Fr, in UpdateNoteInput::new argument order:
+//   op_pub (amount, token, user) | new_note_hash | merkle_root | new_note[4] | old_note[4] |
+//   path_shape[H] | path[H] | op_priv.user | old_account (token0, balance0, token1, balance1)
+__global__ void __launch_bounds__(32) update_note_witness_kernel(const Fr* __restrict__ inputs, uint32_t n_proofs,
+                                                                uint32_t H, int kind, uint32_t num_vars,
+                                                                const PoseidonConsts* __restrict__ pc,
+                                                                Fr* __restrict__ z_all, uint32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & (GROUP - 1);
+    const uint32_t proof_raw = blockIdx.x * (32 / GROUP) + (lane / GROUP);
+    const bool active = proof_raw < n_proofs;
+    const uint32_t proof = active ? proof_raw : n_proofs - 1;  // idle groups shadow the last proof, no stores
+    const uint32_t n_in = 18 + 2 * H;
+    const Fr* in = inputs + (size_t)proof * n_in;
+    Fr* z = z_all + (size_t)proof * num_vars;
+    // input slots
+    const int I_AMOUNT = 0, I_TOKEN = 1, I_USER = 2, I_NNH = 3, I_ROOT = 4, I_NEW = 5, I_OLD = 9;
+    const int I_SHAPE = 13, I_PATH = 13 + H, I_PRIV = 13 + 2 * H, I_ACC = 14 + 2 * H;
+    const bool wr = active && l == 0;  // the lane that writes scalar witnesses
+    bool ok = true;
+    uint32_t cur = 0;
+    // ---- z[0] = 1, instance variables, loaded witnesses
+    if (wr) {
+        st_fr(z + 0, Fr::one());
+        st_fr(z + 1, ld_fr(in + I_AMOUNT));
+        st_fr(z + 2, ld_fr(in + I_TOKEN));
+        st_fr(z + 3, ld_fr(in + I_USER));
+        st_fr(z + 4, ld_fr(in + I_NNH));
+        st_fr(z + 5, ld_fr(in + I_ROOT));
+        st_fr(z + 6, ld_fr(in + I_OLD + 2));  // old_note.nullifier
+    }
+    cur = 7;
+    if (active) {
+        // new_note[4], old zk_id, old trapdoor, old account_hash, path_shape[H], path[H], op_priv, account[4]
+        const uint32_t n_copy = 4 + 3 + 2 * H + 1 + 4;
+        for (uint32_t i = l; i < n_copy; i += GROUP) {
+            uint32_t src;
+            if (i < 4) src = I_NEW + i;
+            else if (i < 7) src = I_OLD + (i == 4 ? 0 : i == 5 ? 1 : 3);
+            else src = I_SHAPE + (i - 7);  // shape, path, op_priv, account are contiguous in the input
+            st_fr(z + cur + i, ld_fr(in + src));
+        }
+    }
+    cur += 4 + 3 + 2 * H + 1 + 4;
+
+    // ---- H(new_note) == new_note_hash                               update_note.rs:129
+    Fr h_new = poseidon_hash(4, [&](int i) { return ld_fr(in + I_NEW + i); }, l, pc, active ? z + cur : nullptr);
+    cur += 2 * host::POSEIDON_TRACE;
+    ok = ok && (h_new == ld_fr(in + I_NNH));
+    // ---- old_note_hash                                               update_note.rs:131
+    Fr current = poseidon_hash(4, [&](int i) { return ld_fr(in + I_OLD + i); }, l, pc, active ? z + cur : nullptr);
+    cur += 2 * host::POSEIDON_TRACE;
+    // ---- Merkle path                                                 merkle_proof.rs:49-57
+    for (uint32_t i = 0; i < H; i++) {
+        const Fr shape = ld_fr(in + I_SHAPE + i);
+        const Fr sib = ld_fr(in + I_PATH + i);
+        const bool sel = shape.is_zero();  // selector = is_zero(shape)
+        if (wr) {
+            Fr inv = sel ? Fr::zero() : (shape == Fr::one() ? Fr::one() : fp_inv(shape));
+            st_fr(z + cur, inv);
+            st_fr(z + cur + 1, sel ? Fr::one() : Fr::zero());
+        }
+        cur += 2;
+        // left = select(sibling, current, selector) ; right = select(current, sibling, selector)
+        const Fr t1 = sel ? fp_sub(sib, current) : Fr::zero();
+        const Fr t2 = sel ? fp_sub(current, sib) : Fr::zero();
+        if (wr) {
+            st_fr(z + cur, t1);
+            st_fr(z + cur + 1, t2);
+        }
+        cur += 2;
+        const Fr left = fp_add(t1, current), right = fp_add(t2, sib);
+        current = poseidon_hash(2, [&](int k) { return k == 0 ? left : right; }, l, pc, active ? z + cur : nullptr);
+        cur += host::POSEIDON_TRACE;
+    }
+    ok = ok && (current == ld_fr(in + I_ROOT));                        // merkle_proof.rs:59-60
+    ok = ok && (ld_fr(in + I_USER) == ld_fr(in + I_PRIV));             // combine(): ops.rs:47-62
+    // ---- H(old_account) == old_note.account_hash                     update_account.rs:79-85
+    Fr h_acc = poseidon_hash(4, [&](int i) { return ld_fr(in + I_ACC + i); }, l, pc, active ? z + cur : nullptr);
+    cur += 2 * host::POSEIDON_TRACE;
+    ok = ok && (h_acc == ld_fr(in + I_OLD + 3));
+    // ---- account update                                              account.rs:36-79 (mock)
+    const Fr amount = ld_fr(in + I_AMOUNT);
+    const Fr token = ld_fr(in + I_TOKEN);
+    {
+        const Fr canon = fp_from_mont(amount);
+        ok = ok && fits_bits128(canon);
+        if (active)
+            for (int b = l; b < host::BALANCE_BITS; b += GROUP)
+                st_fr(z + cur + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
+        cur += host::BALANCE_BITS;
+    }
+    Fr new_bal[2];
+    int n_match = 0;
+    for (int i = 0; i < 2; i++) {
+        const Fr tok = ld_fr(in + I_ACC + 2 * i), bal = ld_fr(in + I_ACC + 2 * i + 1);
+        const Fr diff = fp_sub(tok, token);
+        const bool eq = diff.is_zero();
+        n_match += eq ? 1 : 0;
+        const Fr delta = eq ? amount : Fr::zero();
+        if (wr) {
+            st_fr(z + cur, eq ? Fr::zero() : fp_inv(diff));
+            st_fr(z + cur + 1, eq ? Fr::one() : Fr::zero());
+            st_fr(z + cur + 2, delta);
+        }
+        cur += 3;
+        new_bal[i] = kind == host::KIND_DEPOSIT ? fp_add(bal, delta) : fp_sub(bal, delta);
+        const Fr canon = fp_from_mont(new_bal[i]);
+        ok = ok && fits_bits128(canon);                                // checked_add / checked_sub
+        if (active)
+            for (int b = l; b < host::BALANCE_BITS; b += GROUP)
+                st_fr(z + cur + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
+        cur += host::BALANCE_BITS;
+    }
+    ok = ok && n_match == 1;
+    // ---- H(new_account) == new_note.account_hash                     update_account.rs:88-94
+    Fr h_nacc = poseidon_hash(
+        4, [&](int i) { return (i & 1) ? new_bal[i >> 1] : ld_fr(in + I_ACC + i); }, l, pc, active ? z + cur : nullptr);
+    cur += 2 * host::POSEIDON_TRACE;
+    ok = ok && (h_nacc == ld_fr(in + I_NEW + 3));
+    if (wr) status[proof] = (ok ? 0u : 1u) | (cur == num_vars ? 0u : 2u);
+}
+
+// n_hashes independent hash_fix_len_array calls of the same arity (Merkle tree levels, note hashes)
+__global__ void __launch_bounds__(32) poseidon_hash_batch_kernel(const Fr* __restrict__ in, size_t n_hashes,
+                                                                uint32_t arity,
+                                                                const PoseidonConsts* __restrict__ pc,
+                                                                Fr* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int l = lane & (GROUP - 1);
+    const size_t raw = (size_t)blockIdx.x * (32 / GROUP) + (lane / GROUP);
+    const bool active = raw < n_hashes;
+    const size_t idx = active ? raw : n_hashes - 1;
+    const Fr* src = in + idx * arity;
+    Fr h = poseidon_hash((int)arity, [&](int i) { return ld_fr(src + i); }, l, pc, nullptr);
+    if (active && l == 0) st_fr(out + idx, h);
+}
+
+}  // namespace
+
+namespace b200zk {
+
+int poseidon_consts_device(b200zk_ctx* ctx, const PoseidonConsts** out) {
+    if (!ctx->poseidon_consts) {
+        const PoseidonConsts& pc = host::poseidon_consts();
+        B200ZK_CUDA(ctx, cudaMalloc(&ctx->poseidon_consts, sizeof(PoseidonConsts)));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(ctx->poseidon_consts, &pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = (const PoseidonConsts*)ctx->poseidon_consts;
+    return B200ZK_OK;
+}
+
+// d_inputs: batch * (18 + 2H) Fr; d_z: batch * num_vars Fr; d_status: batch u32
+int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs,
+                               size_t batch, Fr* d_z, uint32_t* d_status) {
+    const PoseidonConsts* pc;
+    B200ZK_TRY(poseidon_consts_device(ctx, &pc));
+    {
+        ProfScope ps(ctx, "witness");
+        update_note_witness_kernel<<<div_up(batch, 32 / GROUP), 32, 0, ctx->stream>>>(d_inputs, (uint32_t)batch, H, kind,
+                                                                                     num_vars, pc, d_z, d_status);
+    }
+    return check_launch(ctx, "update_note_witness_kernel");
+}
+
+}  // namespace b200zk
+
+extern "C" {
+
+int b200zk_poseidon_constants(uint8_t* round_constants, uint8_t* mds) {
+    const PoseidonConsts& pc = host::poseidon_consts();
+    if (round_constants) memcpy(round_constants, pc.rc, sizeof(pc.rc));
+    if (mds) memcpy(mds, pc.mds, sizeof(pc.mds));
+    return B200ZK_OK;
+}
+
+int b200zk_update_note_r1cs(int kind, uint32_t tree_height, b200zk_r1cs** out) {
+    if (!out || (kind != 0 && kind != 1) || tree_height == 0 || tree_height > 64) return B200ZK_ERR_BAD_ARG;
+    b200zk_r1cs* r = new b200zk_r1cs();
+    r->cs = host::synthesize_update_note(kind, tree_height);
+    *out = r;
+    return B200ZK_OK;
+}
+
+void b200zk_r1cs_free(b200zk_r1cs* r) { delete r; }
+
+int b200zk_r1cs_shape(const b200zk_r1cs* r, uint64_t* num_constraints, uint64_t* num_inputs, uint64_t* num_aux,
+                      uint64_t nnz[3]) {
+    if (!r) return B200ZK_ERR_BAD_ARG;
+    if (num_constraints) *num_constraints = r->cs.A.size();
+    if (num_inputs) *num_inputs = r->cs.num_inputs;
+    if (num_aux) *num_aux = r->cs.num_aux;
+    if (nnz) {
+        const std::vector<host::LC>* M[3] = {&r->cs.A, &r->cs.B, &r->cs.C};
+        for (int m = 0; m < 3; m++) {
+            uint64_t c = 0;
+            for (auto& row : *M[m]) c += row.t.size();
+            nnz[m] = c;
+        }
+    }
+    return B200ZK_OK;
+}
+
+int b200zk_r1cs_matrix(const b200zk_r1cs* r, int which, uint64_t* row_ptr, uint32_t* cols, uint8_t* vals) {
+    if (!r || which < 0 || which > 2 || !row_ptr || !cols || !vals) return B200ZK_ERR_BAD_ARG;
+    const std::vector<host::LC>& M = which == 0 ? r->cs.A : which == 1 ? r->cs.B : r->cs.C;
+    uint64_t k = 0;
+    for (size_t i = 0; i < M.size(); i++) {
+        row_ptr[i] = k;
+        for (auto& e : M[i].t) {
+            cols[k] = e.first;
+            memcpy(vals + k * 32, &e.second, 32);
+            k++;
+        }
+    }
+    row_ptr[M.size()] = k;
+    return B200ZK_OK;
+}
+
+int b200zk_poseidon_hash_batch(b200zk_ctx* ctx, const uint8_t* inputs, size_t n_hashes, uint32_t arity, uint8_t* out) {
+    if (!ctx || !inputs || !out || arity == 0 || arity > 64) return B200ZK_ERR_BAD_ARG;
+    if (n_hashes == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const PoseidonConsts* pc;
+    B200ZK_TRY(poseidon_consts_device(ctx, &pc));
+    void *din, *dout;
+    B200ZK_TRY(scratch(ctx, "pos_in", n_hashes * arity * 32, &din));
+    B200ZK_TRY(scratch(ctx, "pos_out", n_hashes * 32, &dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, n_hashes * arity * 32, cudaMemcpyHostToDevice, ctx->stream));
+    poseidon_hash_batch_kernel<<<div_up(n_hashes, 32 / GROUP), 32, 0, ctx->stream>>>((const Fr*)din, n_hashes, arity, pc,
+                                                                                    (Fr*)dout);
+    B200ZK_TRY(check_launch(ctx, "poseidon_hash_batch_kernel"));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, dout, n_hashes * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
+                                     uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status) {
+    if (!ctx || !r || !inputs) return B200ZK_ERR_BAD_ARG;
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t H = r->cs.tree_height, nv = r->cs.num_variables();
+    const size_t in_bytes = batch * (18 + 2 * (size_t)H) * 32, z_bytes = batch * (size_t)nv * 32;
+    void *din, *dz = d_out_assignments, *dst;
+    B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
+    if (!dz) B200ZK_TRY(scratch(ctx, "wit_z", z_bytes, &dz));
+    B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(update_note_witness_device(ctx, r->cs.kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
+    std::vector<uint32_t> st(batch);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_assignments)
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(out_assignments, dz, z_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = B200ZK_OK;
+    for (size_t i = 0; i < batch; i++) {
+        if (out_status) out_status[i] = (uint8_t)st[i];
+        if (st[i] & 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "witness layout does not match the R1CS (internal error)");
+        if (st[i] & 1) rc = B200ZK_ERR_UNSATISFIED;
+    }
+    if (rc != B200ZK_OK) fail(ctx, rc, "a witness does not satisfy the update-note relation (see out_status)");
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,34 @@
+// Opaque handle types of the C ABI and the entry points translation units share.
+#pragma once
+#include "common.cuh"
+#include "ec.cuh"
+#include "host_r1cs.hpp"
+
+struct b200zk_bases {
+    int group = 0;             // 1 = G1, 2 = G2
+    size_t n = 0;              // points per window
+    void* d_points = nullptr;  // Affine<F>[n * (precomputed ? windows : 1)]
+    int precomputed = 0;
+    uint32_t c = 0, windows = 0;
+};
+
+struct b200zk_r1cs {
+    b200zk::host::R1CS cs;
+};
+
+namespace b200zk {
+
+// ntt.cu
+int ntt_device(b200zk_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const Fr* coset_offset, size_t batch);
+// msm.cu (explicitly instantiated for Fq and Fq2)
+template <class F>
+int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride, size_t batch,
+               bool mont, Affine<F>* d_out);
+template <class F>
+int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,
+                size_t n, int precompute);
+// relation.cu
+int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs, size_t batch,
+                               Fr* d_z, uint32_t* d_status);
+
+}  // namespace b200zk

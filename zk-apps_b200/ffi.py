@@ -71,6 +71,20 @@ def lib() -> C.CDLL:
             "b200zk_bases_from_device": (i32, [vp, i32, vp, sz, i32, C.POINTER(vp)]),
             "b200zk_bases_free": (None, [vp, vp]),
             "b200zk_msm_resident": (i32, [vp, vp, vp, i32, sz, sz, vp, vp]),
+            "b200zk_update_note_r1cs": (i32, [i32, u32, C.POINTER(vp)]),
+            "b200zk_r1cs_free": (None, [vp]),
+            "b200zk_r1cs_shape": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64 * 3)]),
+            "b200zk_r1cs_matrix": (i32, [vp, i32, vp, vp, vp]),
+            "b200zk_poseidon_constants": (i32, [vp, vp]),
+            "b200zk_poseidon_hash_batch": (i32, [vp, vp, sz, u32, vp]),
+            "b200zk_update_note_witness_batch": (i32, [vp, vp, vp, sz, vp, vp, vp]),
+            "b200zk_pk_upload": (i32, [vp, vp] + [vp] * 10 + [i32, C.POINTER(vp)]),
+            "b200zk_groth16_setup": (i32, [vp, vp, vp, i32, C.POINTER(vp), vp]),
+            "b200zk_pk_free": (None, [vp, vp]),
+            "b200zk_pk_export_query": (i32, [vp, vp, i32, vp, C.POINTER(sz)]),
+            "b200zk_groth16_prove_batch": (i32, [vp, vp, vp, i32, sz, vp, vp, vp, vp]),
+            "b200zk_update_note_prove_batch": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             if hasattr(L, name):
@@ -288,3 +302,164 @@ class Radix2EvaluationDomain:
         off, keep = _buf(self.offset)
         self.ctx.check(lib().b200zk_ntt_fr_device(self.ctx.handle, C.c_void_p(dptr), self.log_size,
                                                   1 if inverse else 0, off, batch))
+
+
+# ----------------------------------------------------------------------------- relation + Groth16
+DEPOSIT, WITHDRAW = 0, 1
+
+
+def poseidon_constants():
+    """(round constants 64x5, MDS 5x5) as Montgomery bytes -- host-side Grain LFSR of the library."""
+    rc = np.zeros(64 * 5 * 32, dtype=np.uint8)
+    mds = np.zeros(25 * 32, dtype=np.uint8)
+    rcode = lib().b200zk_poseidon_constants(rc.ctypes.data_as(C.c_void_p), mds.ctypes.data_as(C.c_void_p))
+    if rcode != 0:
+        raise B200zkError(rcode, "poseidon_constants")
+    return rc, mds
+
+
+class UpdateNoteRelation:
+    """The R1CS of update_note_circuit (shielder/relations/src/relations/update_note.rs:106-149):
+    the ConstraintSynthesizer of this backend.  Host-only; needs no GPU."""
+
+    def __init__(self, kind: int = WITHDRAW, tree_height: int = 10):
+        self.kind, self.tree_height = kind, tree_height
+        self._h = C.c_void_p()
+        rc = lib().b200zk_update_note_r1cs(kind, tree_height, C.byref(self._h))
+        if rc != 0:
+            raise B200zkError(rc, "b200zk_update_note_r1cs")
+        nc, ni, na = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        nnz = (C.c_uint64 * 3)()
+        lib().b200zk_r1cs_shape(self._h, C.byref(nc), C.byref(ni), C.byref(na), C.byref(nnz))
+        self.num_constraints, self.num_inputs, self.num_aux = nc.value, ni.value, na.value
+        self.num_variables = ni.value + na.value
+        self.nnz = list(nnz)
+        self.n_inputs_per_proof = 18 + 2 * tree_height
+
+    @property
+    def handle(self):
+        return self._h
+
+    def matrix(self, which: int):
+        """-> (row_ptr uint64[nc+1], cols uint32[nnz], vals uint8[nnz*32])"""
+        rp = np.zeros(self.num_constraints + 1, dtype=np.uint64)
+        cols = np.zeros(max(1, self.nnz[which]), dtype=np.uint32)
+        vals = np.zeros(max(1, self.nnz[which]) * 32, dtype=np.uint8)
+        rc = lib().b200zk_r1cs_matrix(self._h, which, rp.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p),
+                                      vals.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise B200zkError(rc, "b200zk_r1cs_matrix")
+        return rp, cols[:self.nnz[which]], vals[:self.nnz[which] * 32]
+
+    def witness_batch(self, ctx: Context, inputs, batch: int, device_out: int | None = None, want_host: bool = True):
+        """K6: full assignments z (batch * num_variables * 32 B) and per-instance status."""
+        pi, ki = _buf(inputs)
+        out = np.zeros(batch * self.num_variables * 32, dtype=np.uint8) if want_host else None
+        status = np.zeros(batch, dtype=np.uint8)
+        rc = lib().b200zk_update_note_witness_batch(
+            ctx.handle, self._h, pi, batch, out.ctypes.data_as(C.c_void_p) if want_host else None,
+            C.c_void_p(device_out) if device_out else None, status.ctypes.data_as(C.c_void_p))
+        if rc not in (0, -6):
+            ctx.check(rc)
+        return out, status
+
+    def free(self):
+        if self._h:
+            lib().b200zk_r1cs_free(self._h)
+            self._h = None
+
+    __del__ = free
+
+
+def poseidon_hash_batch(ctx: Context, inputs, arity: int) -> np.ndarray:
+    pi, ki = _buf(inputs)
+    n = ki.nbytes // (32 * arity)
+    out = np.zeros(n * 32, dtype=np.uint8)
+    ctx.check(lib().b200zk_poseidon_hash_batch(ctx.handle, pi, n, arity, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+class ProvingKey:
+    """Device-resident ark_groth16::ProvingKey + constraint matrices."""
+
+    def __init__(self, ctx: Context, relation: UpdateNoteRelation, handle, vk: np.ndarray | None):
+        self.ctx, self.relation, self._h, self.vk = ctx, relation, handle, vk
+
+    def export_query(self, which: int) -> np.ndarray:
+        cnt = C.c_size_t()
+        self.ctx.check(lib().b200zk_pk_export_query(self.ctx.handle, self._h, which, None, C.byref(cnt)))
+        out = np.zeros(cnt.value * (192 if which == 2 else 96), dtype=np.uint8)
+        self.ctx.check(lib().b200zk_pk_export_query(self.ctx.handle, self._h, which, out.ctypes.data_as(C.c_void_p),
+                                                    C.byref(cnt)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().b200zk_pk_free(self.ctx.handle, self._h)
+            self._h = None
+
+    __del__ = free
+
+
+class Groth16:
+    """ark_groth16::Groth16::<Bls12_381> call sites (names per arkworks 0.4 [recall])."""
+
+    @staticmethod
+    def generate_parameters_with_toxic_waste(ctx: Context, relation: UpdateNoteRelation, toxic, precompute=True):
+        """toxic = (alpha, beta, gamma, delta, tau) ints.  -> ProvingKey (vk bytes in .vk)."""
+        tb = b"".join(int(t % R_MOD).to_bytes(32, "little") for t in toxic)
+        h = C.c_void_p()
+        vk = np.zeros(672 + relation.num_inputs * 96, dtype=np.uint8)
+        pt, kt = _buf(tb)
+        ctx.check(lib().b200zk_groth16_setup(ctx.handle, relation.handle, pt, 1 if precompute else 0, C.byref(h),
+                                             vk.ctypes.data_as(C.c_void_p)))
+        return ProvingKey(ctx, relation, h, vk)
+
+    @staticmethod
+    def pk_upload(ctx: Context, relation: UpdateNoteRelation, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2,
+                  a_query, b_g1_query, b_g2_query, l_query, h_query, precompute=True):
+        bufs = [_buf(x) for x in (alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query, b_g2_query,
+                                  l_query, h_query)]
+        h = C.c_void_p()
+        ctx.check(lib().b200zk_pk_upload(ctx.handle, relation.handle, *[b[0] for b in bufs], 1 if precompute else 0,
+                                         C.byref(h)))
+        return ProvingKey(ctx, relation, h, None)
+
+    @staticmethod
+    def create_proof_with_reduction(pk: ProvingKey, assignments, r, s, batch: int = 1, device_ptr: int | None = None,
+                                    want_points: bool = False):
+        """assignments: batch full assignments z (Montgomery bytes) or a device pointer; r, s: lists of
+        ints (one per proof).  -> proofs (batch x 192 B) [, affine points (batch x 384 B)]."""
+        ctx = pk.ctx
+        rb = np.frombuffer(b"".join(int(x % R_MOD).to_bytes(32, "little") for x in r), dtype=np.uint8)
+        sb = np.frombuffer(b"".join(int(x % R_MOD).to_bytes(32, "little") for x in s), dtype=np.uint8)
+        proofs = np.zeros(batch * 192, dtype=np.uint8)
+        points = np.zeros(batch * 384, dtype=np.uint8) if want_points else None
+        if device_ptr is not None:
+            pa, on_dev = C.c_void_p(device_ptr), 1
+        else:
+            pa, ka = _buf(assignments)
+            on_dev = 0
+        ctx.check(lib().b200zk_groth16_prove_batch(ctx.handle, pk._h, pa, on_dev, batch, rb.ctypes.data_as(C.c_void_p),
+                                                   sb.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
+                                                   points.ctypes.data_as(C.c_void_p) if want_points else None))
+        return (proofs, points) if want_points else proofs
+
+    @staticmethod
+    def prove_update_note(pk: ProvingKey, inputs, r, s, batch: int):
+        """Witness generation (K6) + proving in one call: the user-facing path.  r, s: uint8 arrays
+        (batch x 32 B canonical) or lists of ints."""
+        ctx = pk.ctx
+        def scal(x):
+            if isinstance(x, np.ndarray):
+                return x
+            return np.frombuffer(b"".join(int(v % R_MOD).to_bytes(32, "little") for v in x), dtype=np.uint8)
+        rb, sb = scal(r), scal(s)
+        pi, ki = _buf(inputs)
+        proofs = np.zeros(batch * 192, dtype=np.uint8)
+        status = np.zeros(batch, dtype=np.uint8)
+        rc = lib().b200zk_update_note_prove_batch(ctx.handle, pk._h, pi, batch, rb.ctypes.data_as(C.c_void_p),
+                                                  sb.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
+                                                  status.ctypes.data_as(C.c_void_p))
+        ctx.check(rc)
+        return proofs, status
