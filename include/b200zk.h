@@ -74,6 +74,10 @@ int b200zk_prof_reset(b200zk_ctx* ctx);
 int b200zk_prof_get(b200zk_ctx* ctx, const char* name, double* ms, long* launches);
 int b200zk_prof_names(b200zk_ctx* ctx, char* buf, size_t buflen);   /* comma-separated */
 long b200zk_launch_count(b200zk_ctx* ctx);
+/* work counters accumulated by the kernels' host wrappers, for roofline arithmetic:
+ * "msm_entries_g1"/"msm_entries_g2" = mixed additions issued by msm_accumulate, "msm_buckets_g1/2". */
+int b200zk_stat_get(b200zk_ctx* ctx, const char* name, double* value);
+int b200zk_stat_reset(b200zk_ctx* ctx);
 
 /* ---- K1: field arithmetic test entry points ----------------------------------------------
  * Element-wise out[i] = a[i] op b[i] on the GPU.  Replaces nothing in the reference (row a10);
@@ -185,6 +189,10 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
                                uint8_t* points_out);
 int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
                                    const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status);
+/* same with the instance inputs already resident in device memory (r, s, proofs stay host buffers) */
+int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,
+                                          const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                          uint8_t* out_status);
 
 #ifdef __cplusplus
 }

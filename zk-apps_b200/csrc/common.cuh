@@ -40,6 +40,7 @@ struct b200zk_ctx {
     std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     long launches = 0;                                     // every kernel launch of this library
+    std::map<std::string, double> stats;                   // work counters (b200zk_stat_get)
     void* poseidon_consts = nullptr;                       // device copy, see poseidon.cu
 };
 

@@ -136,4 +136,17 @@ int b200zk_prof_names(b200zk_ctx* ctx, char* buf, size_t buflen) {
 
 long b200zk_launch_count(b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int b200zk_stat_get(b200zk_ctx* ctx, const char* name, double* value) {
+    if (!ctx || !name || !value) return B200ZK_ERR_BAD_ARG;
+    auto it = ctx->stats.find(name);
+    *value = it == ctx->stats.end() ? 0.0 : it->second;
+    return B200ZK_OK;
+}
+
+int b200zk_stat_reset(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_ERR_BAD_ARG;
+    ctx->stats.clear();
+    return B200ZK_OK;
+}
+
 }  // extern "C"

@@ -547,18 +547,20 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
     return groth16_prove_device(ctx, pk, dz, batch, r, s, proofs_out, points_out);
 }
 
-int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
-                                   const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {
+static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, int inputs_on_device,
+                                  size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                  uint8_t* out_status) {
     if (!ctx || !pk || !inputs || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
     if (batch == 0) return B200ZK_OK;
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t H = pk->tree_height, nv = pk->num_inputs + pk->num_aux;
     const size_t in_bytes = batch * (18 + 2 * (size_t)H) * 32;
-    void *din, *dz, *dst;
-    B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
+    void *din = (void*)inputs, *dz, *dst;
+    if (!inputs_on_device) B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
     B200ZK_TRY(scratch(ctx, "g16_z", batch * (size_t)nv * sizeof(Fr), &dz));
     B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!inputs_on_device)
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_TRY(update_note_witness_device(ctx, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
     std::vector<uint32_t> st(batch);
     B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -572,6 +574,17 @@ int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const u
     // like arkworks, an unsatisfied instance is an error, not a proof (SynthesisError::Unsatisfiable in debug builds)
     if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the update-note relation");
     return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, r, s, proofs_out, nullptr);
+}
+
+int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
+                                   const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {
+    return prove_update_note_impl(ctx, pk, inputs, 0, batch, r, s, proofs_out, out_status);
+}
+
+int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,
+                                          const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                          uint8_t* out_status) {
+    return prove_update_note_impl(ctx, pk, (const uint8_t*)d_inputs, 1, batch, r, s, proofs_out, out_status);
 }
 
 }  // extern "C"

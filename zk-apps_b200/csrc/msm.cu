@@ -473,9 +473,15 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
                                                                     (uint32_t*)d_tasks);
         B200ZK_TRY(check_launch(ctx, "msm_task_list"));
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, ctx->stream));
+        uint32_t n_entries = 0;
         B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_tasks, (const uint32_t*)d_toff + n_keys, 4, cudaMemcpyDeviceToHost,
                                          ctx->stream));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_entries, (const uint32_t*)d_offsets + n_keys, 4, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
         B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // work counters for the roofline: mixed additions and buckets of this launch
+        ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_entries_g1" : "msm_entries_g2"] += n_entries;
+        ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2"] += n_keys;
     }
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_partials_g1" : "msm_partials_g2",
                        ((size_t)n_tasks + 1) * sizeof(XYZZ<F>), &d_partials));

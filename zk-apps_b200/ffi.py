@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
             "b200zk_pk_export_query": (i32, [vp, vp, i32, vp, C.POINTER(sz)]),
             "b200zk_groth16_prove_batch": (i32, [vp, vp, vp, i32, sz, vp, vp, vp, vp]),
             "b200zk_update_note_prove_batch": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
+            "b200zk_update_note_prove_batch_device": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
+            "b200zk_stat_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double)]),
+            "b200zk_stat_reset": (i32, [vp]),
         }
         for name, (res, args) in sig.items():
             if hasattr(L, name):
@@ -180,6 +183,17 @@ class Context:
 
     def launch_count(self) -> int:
         return lib().b200zk_launch_count(self._h)
+
+    def stat_get(self, name: str) -> float:
+        v = C.c_double()
+        self.check(lib().b200zk_stat_get(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+    def stat_reset(self):
+        self.check(lib().b200zk_stat_reset(self._h))
+
+    def stream_ptr(self) -> int:
+        return lib().b200zk_stream(self._h)
 
     # ---- K1 debug
     def field_op(self, field: int, op: int, a, b=None) -> np.ndarray:
@@ -444,6 +458,18 @@ class Groth16:
                                                    sb.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
                                                    points.ctypes.data_as(C.c_void_p) if want_points else None))
         return (proofs, points) if want_points else proofs
+
+    @staticmethod
+    def prove_update_note_device(pk: ProvingKey, d_inputs: int, rb: np.ndarray, sb: np.ndarray, batch: int,
+                                 proofs: np.ndarray | None = None):
+        """Same as prove_update_note with the instance inputs already in device memory."""
+        ctx = pk.ctx
+        if proofs is None:
+            proofs = np.zeros(batch * 192, dtype=np.uint8)
+        ctx.check(lib().b200zk_update_note_prove_batch_device(ctx.handle, pk._h, C.c_void_p(d_inputs), batch,
+                                                              rb.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p),
+                                                              proofs.ctypes.data_as(C.c_void_p), None))
+        return proofs
 
     @staticmethod
     def prove_update_note(pk: ProvingKey, inputs, r, s, batch: int):
