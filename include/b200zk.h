@@ -57,6 +57,9 @@ int b200zk_init(int device, b200zk_ctx** out);
 void b200zk_destroy(b200zk_ctx* ctx);
 const char* b200zk_last_error(b200zk_ctx* ctx);
 int b200zk_sync(b200zk_ctx* ctx);
+/* options: "concurrency" (default 1): run the independent MSMs of a proof batch on auxiliary
+ * streams; 0 serialises everything on the ctx stream (used for per-kernel profiling). */
+int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value);
 /* raw device memory for callers that keep operands resident in HBM */
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** dptr);
 int b200zk_dev_free(b200zk_ctx* ctx, void* dptr);

@@ -29,7 +29,11 @@ struct DeviceBuf {
 struct b200zk_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                         // main stream (slot 0)
+    static constexpr int AUX_STREAMS = 4;                  // slots 1..4: independent MSMs of one proof batch
+    cudaStream_t aux[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    bool concurrency = true;                               // b200zk_set_option("concurrency")
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
     std::map<uint64_t, b200zk::DeviceBuf> tables;          // twiddle / coset tables, keyed
@@ -66,9 +70,13 @@ inline int fail(b200zk_ctx* ctx, int code, const std::string& msg) {
         if (_rc != B200ZK_OK) return _rc; \
     } while (0)
 
-// grow-only named scratch allocation
-inline int scratch(b200zk_ctx* ctx, const char* name, size_t bytes, void** out) {
-    DeviceBuf& b = ctx->scratch[name];
+inline cudaStream_t slot_stream(b200zk_ctx* ctx, int slot) {
+    return (slot <= 0 || !ctx->concurrency) ? ctx->stream : ctx->aux[(slot - 1) % b200zk_ctx::AUX_STREAMS];
+}
+
+// grow-only named scratch allocation (slot > 0: a private copy for work running on an aux stream)
+inline int scratch(b200zk_ctx* ctx, const char* name, size_t bytes, void** out, int slot = 0) {
+    DeviceBuf& b = ctx->scratch[slot > 0 ? std::string(name) + "#" + std::to_string(slot) : std::string(name)];
     if (b.bytes < bytes) {
         if (b.ptr) B200ZK_CUDA(ctx, cudaFree(b.ptr));
         b.ptr = nullptr;
@@ -108,16 +116,17 @@ struct ProfScope {
         cudaEventCreate(&e);
         return e;
     }
-    ProfScope(b200zk_ctx* c, const char* n) : ctx(c), name(n) {
+    cudaStream_t st;
+    ProfScope(b200zk_ctx* c, const char* n, cudaStream_t s = nullptr) : ctx(c), name(n), st(s ? s : c->stream) {
         if (ctx->prof_enabled) {
             a = get_event(ctx);
             b = get_event(ctx);
-            cudaEventRecord(a, ctx->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~ProfScope() {
         if (ctx->prof_enabled) {
-            cudaEventRecord(b, ctx->stream);
+            cudaEventRecord(b, st);
             ctx->prof_pending.emplace_back(name, a, b);
         }
     }

@@ -23,14 +23,40 @@ int b200zk_init(int device, b200zk_ctx** out) {
         delete ctx;
         return B200ZK_ERR_CUDA;
     }
+    for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return B200ZK_ERR_CUDA;
+        }
+    }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return B200ZK_ERR_CUDA;
+    }
     *out = ctx;
     return B200ZK_OK;
+}
+
+int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return B200ZK_ERR_BAD_ARG;
+    if (strcmp(name, "concurrency") == 0) {
+        cudaDeviceSynchronize();
+        ctx->concurrency = value != 0;
+        return B200ZK_OK;
+    }
+    return fail(ctx, B200ZK_ERR_BAD_ARG, std::string("unknown option ") + name);
 }
 
 void b200zk_destroy(b200zk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto& kv : ctx->scratch)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto& kv : ctx->tables)
@@ -85,6 +111,7 @@ void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 
 static void prof_resolve(b200zk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) cudaStreamSynchronize(ctx->aux[i]);
     for (auto& t : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)) == cudaSuccess) {

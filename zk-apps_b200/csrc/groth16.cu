@@ -311,7 +311,19 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
     B200ZK_CUDA(ctx, cudaMemcpyAsync(d_r, r, B * 32, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(d_s, s, B * 32, cudaMemcpyHostToDevice, ctx->stream));
     const Singles* sg = (const Singles*)pk->d_singles;
-    // scalar multiples of delta do not depend on the witness: issue them first
+    G1Affine* m1 = (G1Affine*)d_msm1;
+    const uint32_t* zs = (const uint32_t*)d_z;
+    // ---- the four MSMs that only need z run on auxiliary streams, concurrently with H(x) below:
+    //      their latency-bound tails (bucket reduction) hide behind each other's bucket accumulation
+    if (ctx->concurrency) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
+    }
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->a_query, zs, nv, nv, B, true, m1 + 0 * B, 1));
+    B200ZK_TRY(msm_device<Fq2>(ctx, &pk->b_g2_query, zs, nv, nv, B, true, (G2Affine*)d_msm2, 4));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->b_g1_query, zs, nv, nv, B, true, m1 + 1 * B, 2));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->l_query, zs + (size_t)pk->num_inputs * 8, pk->num_aux, nv, B, true, m1 + 2 * B, 3));
+    // scalar multiples of delta do not depend on the witness
     finalize_phase1<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, d_r, d_s, (uint32_t)B, (G1XYZZ*)d_t1, (G2XYZZ*)d_t2);
     B200ZK_TRY(check_launch(ctx, "finalize_phase1"));
 
@@ -338,15 +350,13 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
         B200ZK_TRY(check_launch(ctx, "h_pointwise"));
     }
     B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, true, &g, B));
-
-    // ---- MSMs (scalars in Montgomery form straight from z / h)
-    G1Affine* m1 = (G1Affine*)d_msm1;
-    const uint32_t* zs = (const uint32_t*)d_z;
-    B200ZK_TRY(msm_device<Fq>(ctx, &pk->a_query, zs, nv, nv, B, true, m1 + 0 * B));
-    B200ZK_TRY(msm_device<Fq>(ctx, &pk->b_g1_query, zs, nv, nv, B, true, m1 + 1 * B));
-    B200ZK_TRY(msm_device<Fq>(ctx, &pk->l_query, zs + (size_t)pk->num_inputs * 8, pk->num_aux, nv, B, true, m1 + 2 * B));
-    B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B));
-    B200ZK_TRY(msm_device<Fq2>(ctx, &pk->b_g2_query, zs, nv, nv, B, true, (G2Affine*)d_msm2));
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B, 0));
+    if (ctx->concurrency) {
+        for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
+            B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
+            B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+        }
+    }
 
     // ---- assembly + compression
     {

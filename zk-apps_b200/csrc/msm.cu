@@ -35,22 +35,31 @@ struct Plan {
     bool precomp;
 };
 
-uint32_t pick_window(size_t n) {
-    if (const char* e = getenv("B200ZK_MSM_C")) {
+// Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
+// plus ~4 full additions (14 each) per bucket for the reduction; without precomputed window
+// multiples every window has its own bucket set.
+uint32_t pick_window(size_t n, bool precomp) {
+    if (const char* e = getenv(precomp ? "B200ZK_MSM_C_PRE" : "B200ZK_MSM_C")) {
         int v = atoi(e);
         if (v >= 2 && v <= 22) return (uint32_t)v;
     }
-    uint32_t lg = 0;
-    while ((1ull << (lg + 1)) <= n) lg++;
-    int c = (int)lg - 4;
-    if (c < 3) c = 3;
-    if (c > 18) c = 18;
-    return (uint32_t)c;
+    double best = 1e300;
+    uint32_t best_c = 3;
+    for (uint32_t c = 3; c <= 20; c++) {
+        const double W = (256 + c - 1) / c;
+        const double madds = (double)n * W * 10.0, per_set = (double)(1u << (c - 1)) * 56.0;
+        const double cost = madds + (precomp ? per_set : per_set * W);
+        if (cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    return best_c;
 }
 
 Plan make_plan(size_t n, bool precomp, uint32_t c_fixed) {
     Plan p;
-    p.c = c_fixed ? c_fixed : pick_window(n);
+    p.c = c_fixed ? c_fixed : pick_window(n, precomp);
     p.windows = (256 + p.c - 1) / p.c;
     p.nb = 1u << (p.c - 1);
     p.precomp = precomp;
@@ -221,14 +230,16 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 // of any scalar distribution, 0/1-heavy witnesses, adversarial inputs) cannot serialise the
 // kernel.  A bucket with one task is written straight to `buckets`; the partial sums of a
 // multi-task bucket go to `partials` and are folded by msm_fold_small / msm_fold_big.
-constexpr uint32_t LOG_TASK_LEN = 8, TASK_LEN = 1u << LOG_TASK_LEN;
+// The task length is a power of two near the mean bucket size: every lane of a warp then runs
+// about the same number of additions (ncu: a fixed length of 256 left 50% of the lanes idle).
 constexpr uint32_t FOLD_SMALL_MAX = 8;
 
-__global__ void msm_task_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t* __restrict__ tcount) {
+__global__ void msm_task_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t log_tl,
+                                uint32_t* __restrict__ tcount) {
     uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     uint32_t cnt = offsets[key + 1] - offsets[key];
-    tcount[key] = (cnt + TASK_LEN - 1) >> LOG_TASK_LEN;
+    tcount[key] = (cnt + (1u << log_tl) - 1) >> log_tl;
 }
 
 __global__ void msm_task_list(const uint32_t* __restrict__ toff, uint32_t n_keys, uint32_t* __restrict__ tasks) {
@@ -243,14 +254,17 @@ __global__ void __launch_bounds__(128) msm_accumulate(const Affine<F>* __restric
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ toff,
-                                                      const uint32_t* __restrict__ tasks, uint32_t n_tasks,
-                                                      XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ partials) {
+                                                      const uint32_t* __restrict__ tasks, uint32_t n_keys,
+                                                      uint32_t log_tl, XYZZ<F>* __restrict__ buckets,
+                                                      XYZZ<F>* __restrict__ partials) {
+    // the grid is sized for the worst case; the real task count lives in device memory so the
+    // host never has to wait for it
     uint32_t task = blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= n_tasks) return;
+    if (task >= toff[n_keys]) return;
     const uint32_t key = tasks[task];
     const uint32_t t0 = toff[key], nt = toff[key + 1] - t0;
-    uint32_t k = offsets[key] + ((task - t0) << LOG_TASK_LEN);
-    const uint32_t end = min(k + TASK_LEN, offsets[key + 1]);
+    uint32_t k = offsets[key] + ((task - t0) << log_tl);
+    const uint32_t end = min(k + (1u << log_tl), offsets[key + 1]);
     XYZZ<F> acc = XYZZ<F>::inf();
     uint32_t v = sorted[k];
     Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
@@ -400,15 +414,16 @@ __global__ void apply_inf_flags(Affine<F>* pts, const uint8_t* flags, size_t n) 
     if (i < n && flags[i]) pts[i] = Affine<F>::inf();
 }
 
-int exclusive_scan(b200zk_ctx* ctx, const uint32_t* d_in, size_t n, uint32_t* d_out /* n+1 */) {
+int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, int slot, const uint32_t* d_in, size_t n,
+                   uint32_t* d_out /* n+1 */) {
     const unsigned blocks = div_up(n, SCAN_BLOCK);
     void* bs;
-    B200ZK_TRY(scratch(ctx, "msm_scan_blocks", (size_t)blocks * 4 + 16, &bs));
-    scan_block_sums<<<blocks, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, (uint32_t*)bs);
+    B200ZK_TRY(scratch(ctx, "msm_scan_blocks", (size_t)blocks * 4 + 16, &bs, slot));
+    scan_block_sums<<<blocks, SCAN_THREADS, 0, st>>>(d_in, n, (uint32_t*)bs);
     B200ZK_TRY(check_launch(ctx, "scan_block_sums"));
-    scan_single<<<1, SCAN_THREADS, 0, ctx->stream>>>((uint32_t*)bs, blocks);
+    scan_single<<<1, SCAN_THREADS, 0, st>>>((uint32_t*)bs, blocks);
     B200ZK_TRY(check_launch(ctx, "scan_single"));
-    scan_apply<<<blocks, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, (const uint32_t*)bs, d_out);
+    scan_apply<<<blocks, SCAN_THREADS, 0, st>>>(d_in, n, (const uint32_t*)bs, d_out);
     return check_launch(ctx, "scan_apply");
 }
 
@@ -420,11 +435,13 @@ namespace b200zk {
 // scalars, canonical or Montgomery (`mont`).  d_out: batch affine points.
 template <class F>
 int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride,
-               size_t batch, bool mont, Affine<F>* d_out) {
+               size_t batch, bool mont, Affine<F>* d_out, int slot) {
     if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
     if (batch == 0) return B200ZK_OK;
+    const cudaStream_t st = slot_stream(ctx, slot);
+    if (!ctx->concurrency) slot = 0;
     if (n == 0) {
-        B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), ctx->stream));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), st));
         return B200ZK_OK;
     }
     Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0);
@@ -435,72 +452,73 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     const uint32_t n_keys = (uint32_t)n_keys64;
 
     void *d_counts, *d_offsets, *d_cursor, *d_sorted, *d_buckets, *d_red_a, *d_red_b;
-    B200ZK_TRY(scratch(ctx, "msm_counts", ((size_t)n_keys + 1) * 4, &d_counts));
-    B200ZK_TRY(scratch(ctx, "msm_offsets", ((size_t)n_keys + 1) * 4, &d_offsets));
-    B200ZK_TRY(scratch(ctx, "msm_cursor", ((size_t)n_keys + 1) * 4, &d_cursor));
-    B200ZK_TRY(scratch(ctx, "msm_sorted", (size_t)max_entries * 4, &d_sorted));
+    B200ZK_TRY(scratch(ctx, "msm_counts", ((size_t)n_keys + 1) * 4, &d_counts, slot));
+    B200ZK_TRY(scratch(ctx, "msm_offsets", ((size_t)n_keys + 1) * 4, &d_offsets, slot));
+    B200ZK_TRY(scratch(ctx, "msm_cursor", ((size_t)n_keys + 1) * 4, &d_cursor, slot));
+    B200ZK_TRY(scratch(ctx, "msm_sorted", (size_t)max_entries * 4, &d_sorted, slot));
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2",
-                       (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets));
+                       (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets, slot));
 
     const size_t total = n * batch;
-    B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
     {
-        ProfScope ps(ctx, "msm_sort");
-        msm_count<<<div_up(total, 256), 256, 0, ctx->stream>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+        ProfScope ps(ctx, "msm_sort", st);
+        msm_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
                                                                (uint32_t*)d_counts);
         B200ZK_TRY(check_launch(ctx, "msm_count"));
-        B200ZK_TRY(exclusive_scan(ctx, (const uint32_t*)d_counts, n_keys, (uint32_t*)d_offsets));
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(d_cursor, d_offsets, (size_t)n_keys * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        msm_scatter<<<div_up(total, 256), 256, 0, ctx->stream>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+        B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_counts, n_keys, (uint32_t*)d_offsets));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(d_cursor, d_offsets, (size_t)n_keys * 4, cudaMemcpyDeviceToDevice, st));
+        msm_scatter<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
                                                                  (uint32_t*)d_cursor, (uint32_t*)d_sorted);
         B200ZK_TRY(check_launch(ctx, "msm_scatter"));
     }
     // task list (buckets cut into <= TASK_LEN entries)
     void *d_tcount, *d_toff, *d_tasks, *d_partials, *d_big;
-    const uint64_t max_tasks = (uint64_t)n_keys + (max_entries >> LOG_TASK_LEN) + 1;
-    B200ZK_TRY(scratch(ctx, "msm_tcount", ((size_t)n_keys + 1) * 4, &d_tcount));
-    B200ZK_TRY(scratch(ctx, "msm_toff", ((size_t)n_keys + 1) * 4, &d_toff));
-    B200ZK_TRY(scratch(ctx, "msm_tasks", (size_t)max_tasks * 4, &d_tasks));
-    B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)(max_entries >> LOG_TASK_LEN) / FOLD_SMALL_MAX + 8) * 4, &d_big));
-    uint32_t n_tasks = 0;
+    // task length: power of two >= 1.25 x the mean bucket size, within [16, 256]
+    uint32_t log_tl = 4;
+    while (log_tl < 8 && (double)(1u << log_tl) < 1.25 * (double)max_entries / (double)n_keys) log_tl++;
+    const uint64_t max_tasks = (uint64_t)n_keys + (max_entries >> log_tl) + 1;
+    B200ZK_TRY(scratch(ctx, "msm_tcount", ((size_t)n_keys + 1) * 4, &d_tcount, slot));
+    B200ZK_TRY(scratch(ctx, "msm_toff", ((size_t)n_keys + 1) * 4, &d_toff, slot));
+    B200ZK_TRY(scratch(ctx, "msm_tasks", (size_t)max_tasks * 4, &d_tasks, slot));
+    B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)(max_entries >> log_tl) / FOLD_SMALL_MAX + 8) * 4, &d_big, slot));
     {
-        ProfScope ps(ctx, "msm_tasks");
-        msm_task_counts<<<div_up(n_keys, 256), 256, 0, ctx->stream>>>((const uint32_t*)d_offsets, n_keys,
+        ProfScope ps(ctx, "msm_tasks", st);
+        msm_task_counts<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_offsets, n_keys, log_tl,
                                                                       (uint32_t*)d_tcount);
         B200ZK_TRY(check_launch(ctx, "msm_task_counts"));
-        B200ZK_TRY(exclusive_scan(ctx, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
-        msm_task_list<<<div_up(n_keys, 256), 256, 0, ctx->stream>>>((const uint32_t*)d_toff, n_keys,
+        B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
+        msm_task_list<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_toff, n_keys,
                                                                     (uint32_t*)d_tasks);
         B200ZK_TRY(check_launch(ctx, "msm_task_list"));
-        B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, ctx->stream));
-        uint32_t n_entries = 0;
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_tasks, (const uint32_t*)d_toff + n_keys, 4, cudaMemcpyDeviceToHost,
-                                         ctx->stream));
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_entries, (const uint32_t*)d_offsets + n_keys, 4, cudaMemcpyDeviceToHost,
-                                         ctx->stream));
-        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        // work counters for the roofline: mixed additions and buckets of this launch
-        ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_entries_g1" : "msm_entries_g2"] += n_entries;
-        ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2"] += n_keys;
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, st));
+        if (ctx->prof_enabled) {  // work counters for the roofline (costs a host sync: profiling runs only)
+            uint32_t n_entries = 0;
+            B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_entries, (const uint32_t*)d_offsets + n_keys, 4, cudaMemcpyDeviceToHost, st));
+            B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_entries_g1" : "msm_entries_g2"] += n_entries;
+            ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2"] += n_keys;
+        }
     }
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_partials_g1" : "msm_partials_g2",
-                       ((size_t)n_tasks + 1) * sizeof(XYZZ<F>), &d_partials));
+                       ((size_t)max_tasks + 1) * sizeof(XYZZ<F>), &d_partials, slot));
     uint32_t* big_count = (uint32_t*)d_big;
     uint32_t* big_list = (uint32_t*)d_big + 1;
-    if (n_tasks) {
-        ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2");
-        msm_accumulate<F><<<div_up(n_tasks, 128), 128, 0, ctx->stream>>>(
+    {
+        ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2", st);
+        msm_accumulate<F><<<div_up(max_tasks, 128), 128, 0, st>>>(
             (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
-            (const uint32_t*)d_toff, (const uint32_t*)d_tasks, n_tasks, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
+            (const uint32_t*)d_toff, (const uint32_t*)d_tasks, n_keys, log_tl, (XYZZ<F>*)d_buckets,
+            (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
     }
     {
-        ProfScope ps(ctx, "msm_fold");
-        msm_fold_small<F><<<div_up(n_keys, 64), 64, 0, ctx->stream>>>((const uint32_t*)d_toff, n_keys,
+        ProfScope ps(ctx, "msm_fold", st);
+        msm_fold_small<F><<<div_up(n_keys, 64), 64, 0, st>>>((const uint32_t*)d_toff, n_keys,
                                                                        (const XYZZ<F>*)d_partials, (XYZZ<F>*)d_buckets,
                                                                        big_list, big_count);
         B200ZK_TRY(check_launch(ctx, "msm_fold_small"));
-        msm_fold_big<F><<<ctx->sm_count * 4, 32, 0, ctx->stream>>>((const uint32_t*)d_toff, (const XYZZ<F>*)d_partials,
+        msm_fold_big<F><<<ctx->sm_count * 4, 32, 0, st>>>((const uint32_t*)d_toff, (const XYZZ<F>*)d_partials,
                                                                    (XYZZ<F>*)d_buckets, big_list, big_count);
         B200ZK_TRY(check_launch(ctx, "msm_fold_big"));
     }
@@ -510,11 +528,11 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     while ((1u << log_s) > pl.nb) log_s--;
     const uint32_t chunks_per_set = pl.nb >> log_s;
     const uint32_t n_chunks = sets * chunks_per_set;
-    B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)n_chunks * sizeof(XYZZ<F>), &d_red_a));
-    B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)n_chunks / 8 + sets + 8) * sizeof(XYZZ<F>), &d_red_b));
+    B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)n_chunks * sizeof(XYZZ<F>), &d_red_a, slot));
+    B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)n_chunks / 8 + sets + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
     {
-        ProfScope ps(ctx, "msm_reduce");
-        msm_chunk_reduce<F><<<div_up(n_chunks, 64), 64, 0, ctx->stream>>>((const XYZZ<F>*)d_buckets, pl.nb, log_s,
+        ProfScope ps(ctx, "msm_reduce", st);
+        msm_chunk_reduce<F><<<div_up(n_chunks, 64), 64, 0, st>>>((const XYZZ<F>*)d_buckets, pl.nb, log_s,
                                                                            n_chunks, (XYZZ<F>*)d_red_a);
         B200ZK_TRY(check_launch(ctx, "msm_chunk_reduce"));
         uint32_t m = chunks_per_set;
@@ -523,21 +541,21 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         while (m > 1) {
             const uint32_t R = 8;
             const uint32_t m_out = (m + R - 1) / R;
-            msm_sum<F><<<div_up((size_t)sets * m_out, 64), 64, 0, ctx->stream>>>(src, sets, m, R, dst);
+            msm_sum<F><<<div_up((size_t)sets * m_out, 64), 64, 0, st>>>(src, sets, m, R, dst);
             B200ZK_TRY(check_launch(ctx, "msm_sum"));
             std::swap(src, dst);
             m = m_out;
         }
-        msm_finish<F><<<div_up(batch, 32), 32, 0, ctx->stream>>>(src, (uint32_t)batch, pl.weff, pl.c, d_out);
+        msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(src, (uint32_t)batch, pl.weff, pl.c, d_out);
         B200ZK_TRY(check_launch(ctx, "msm_finish"));
     }
     return B200ZK_OK;
 }
 
 template int msm_device<Fq>(b200zk_ctx*, const b200zk_bases*, const uint32_t*, size_t, size_t, size_t, bool,
-                            Affine<Fq>*);
+                            Affine<Fq>*, int);
 template int msm_device<Fq2>(b200zk_ctx*, const b200zk_bases*, const uint32_t*, size_t, size_t, size_t, bool,
-                             Affine<Fq2>*);
+                             Affine<Fq2>*, int);
 
 template <class F>
 int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,

@@ -23,7 +23,7 @@ int ntt_device(b200zk_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const 
 // msm.cu (explicitly instantiated for Fq and Fq2)
 template <class F>
 int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride, size_t batch,
-               bool mont, Affine<F>* d_out);
+               bool mont, Affine<F>* d_out, int slot = 0);
 template <class F>
 int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,
                 size_t n, int precompute);

@@ -49,6 +49,7 @@ def lib() -> C.CDLL:
             "b200zk_destroy": (None, [vp]),
             "b200zk_last_error": (C.c_char_p, [vp]),
             "b200zk_sync": (i32, [vp]),
+            "b200zk_set_option": (i32, [vp, C.c_char_p, i32]),
             "b200zk_dev_alloc": (i32, [vp, sz, C.POINTER(vp)]),
             "b200zk_dev_free": (i32, [vp, vp]),
             "b200zk_dev_upload": (i32, [vp, vp, vp, sz]),
@@ -145,6 +146,9 @@ class Context:
 
     def sync(self):
         self.check(lib().b200zk_sync(self._h))
+
+    def set_option(self, name: str, value: int):
+        self.check(lib().b200zk_set_option(self._h, name.encode(), int(value)))
 
     # ---- device memory
     def alloc(self, nbytes: int) -> int:
