@@ -10,8 +10,10 @@
 //                   bucket keys  key = (msm_in_batch * windows + window) * 2^(c-1) + |d|-1
 //   2. scan_*:      exclusive prefix sum of the histogram (bucket start offsets)
 //   3. msm_scatter: counting-sort scatter of (point index | sign) into bucket order
-//   4. msm_accumulate: one thread per bucket, mixed additions (XYZZ += affine, 8M+2S) of the
-//                   bucket's points, 128-bit loads, next point prefetched while adding
+//   4. msm_accumulate: one thread per fixed run of 2^log_tl sorted entries (independent of bucket
+//                   boundaries, so all lanes do equal work), mixed additions (XYZZ += affine,
+//                   8M+2S), 128-bit loads, next point prefetched while adding; msm_fold_* sums the
+//                   partials of buckets that span several runs
 //   5. msm_chunk_reduce + msm_sum: weighted bucket sum  sum_j (j+1) B_j  per window by running
 //                   sums over 32-bucket chunks (+ one small scalar multiple per chunk), then a
 //                   log-depth tree of plain sums
@@ -226,59 +228,83 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 }
 
 // ---------------------------------------------------------------- bucket accumulation
-// Buckets are cut into tasks of at most TASK_LEN entries so that one huge bucket (the top window
-// of any scalar distribution, 0/1-heavy witnesses, adversarial inputs) cannot serialise the
-// kernel.  A bucket with one task is written straight to `buckets`; the partial sums of a
-// multi-task bucket go to `partials` and are folded by msm_fold_small / msm_fold_big.
-// The task length is a power of two near the mean bucket size: every lane of a warp then runs
-// about the same number of additions (ncu: a fixed length of 256 left 50% of the lanes idle).
+// The bucket-sorted entry array is cut into fixed runs of L = 2^log_tl entries, one thread per run,
+// whatever the bucket boundaries are: every lane of a warp executes exactly L mixed additions
+// (ncu on the one-thread-per-bucket version: 16-23 of 32 lanes active, because bucket sizes are
+// Poisson distributed and the top window / 0-1-heavy witnesses create huge buckets).  When a run
+// crosses a bucket boundary the running sum is flushed.  A bucket covered by a single run is
+// written straight to `buckets`; a bucket split over several runs gets one partial per run
+// (slot = seg_off[bucket] + run - first_run_of_bucket) folded by msm_fold_small / msm_fold_big.
 constexpr uint32_t FOLD_SMALL_MAX = 8;
 
-__global__ void msm_task_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t log_tl,
-                                uint32_t* __restrict__ tcount) {
+// number of runs each bucket intersects (0 for an empty bucket)
+__global__ void msm_seg_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t log_tl,
+                               uint32_t* __restrict__ scount) {
     uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
-    uint32_t cnt = offsets[key + 1] - offsets[key];
-    tcount[key] = (cnt + (1u << log_tl) - 1) >> log_tl;
+    const uint32_t lo = offsets[key], hi = offsets[key + 1];
+    scount[key] = hi > lo ? ((hi - 1) >> log_tl) - (lo >> log_tl) + 1 : 0;
 }
 
-__global__ void msm_task_list(const uint32_t* __restrict__ toff, uint32_t n_keys, uint32_t* __restrict__ tasks) {
-    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= n_keys) return;
-    const uint32_t lo = toff[key], hi = toff[key + 1];
-    for (uint32_t t = lo; t < hi; t++) tasks[t] = key;
+template <class F>
+__device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_t log_tl, const XYZZ<F>& acc,
+                                             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ soff,
+                                             XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ partials) {
+    const uint32_t s0 = soff[key], ns = soff[key + 1] - s0;
+    if (ns == 1) buckets[key] = acc;
+    else partials[s0 + (run - (offsets[key] >> log_tl))] = acc;
 }
 
 template <class F>
 __global__ void __launch_bounds__(128) msm_accumulate(const Affine<F>* __restrict__ bases,
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ sorted,
-                                                      const uint32_t* __restrict__ toff,
-                                                      const uint32_t* __restrict__ tasks, uint32_t n_keys,
+                                                      const uint32_t* __restrict__ soff, uint32_t n_keys,
                                                       uint32_t log_tl, XYZZ<F>* __restrict__ buckets,
                                                       XYZZ<F>* __restrict__ partials) {
-    // the grid is sized for the worst case; the real task count lives in device memory so the
+    // the grid is sized for the worst case; the real entry count lives in device memory so the
     // host never has to wait for it
-    uint32_t task = blockIdx.x * blockDim.x + threadIdx.x;
-    if (task >= toff[n_keys]) return;
-    const uint32_t key = tasks[task];
-    const uint32_t t0 = toff[key], nt = toff[key + 1] - t0;
-    uint32_t k = offsets[key] + ((task - t0) << log_tl);
-    const uint32_t end = min(k + (1u << log_tl), offsets[key + 1]);
+    const uint32_t run = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = offsets[n_keys];
+    uint32_t k = run << log_tl;
+    if (k >= total) return;
+    const uint32_t end = min(k + (1u << log_tl), total);
+    // bucket of the first entry: the last key with offsets[key] <= k (skips empty buckets)
+    uint32_t lo = 0, hi = n_keys;  // invariant: offsets[lo] <= k < offsets[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (offsets[mid] <= k) lo = mid;
+        else hi = mid;
+    }
+    uint32_t key = lo;
+    uint32_t bend = offsets[key + 1];
     XYZZ<F> acc = XYZZ<F>::inf();
     uint32_t v = sorted[k];
     Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
     bool neg = (v >> 31) != 0;
-    for (k++; k < end; k++) {
-        uint32_t vn = sorted[k];
-        Affine<F> nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
+    for (;;) {
+        const uint32_t kn = k + 1;
+        Affine<F> nxt;
+        uint32_t vn = 0;
+        if (kn < end) {
+            vn = sorted[kn];
+            nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
+        }
         ec_madd(acc, cur, neg);
+        if (kn >= end) break;
+        if (kn == bend) {  // next entry belongs to a later bucket
+            flush_bucket(key, run, log_tl, acc, offsets, soff, buckets, partials);
+            acc = XYZZ<F>::inf();
+            do {
+                key++;
+                bend = offsets[key + 1];
+            } while (bend == kn);
+        }
         cur = nxt;
         neg = (vn >> 31) != 0;
+        k = kn;
     }
-    ec_madd(acc, cur, neg);
-    if (nt == 1) buckets[key] = acc;
-    else partials[task] = acc;
+    flush_bucket(key, run, log_tl, acc, offsets, soff, buckets, partials);
 }
 
 // thread per bucket: empty -> infinity, <= FOLD_SMALL_MAX partials -> summed here, more -> queued
@@ -472,25 +498,21 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
                                                                  (uint32_t*)d_cursor, (uint32_t*)d_sorted);
         B200ZK_TRY(check_launch(ctx, "msm_scatter"));
     }
-    // task list (buckets cut into <= TASK_LEN entries)
-    void *d_tcount, *d_toff, *d_tasks, *d_partials, *d_big;
-    // task length: power of two >= 1.25 x the mean bucket size, within [16, 256]
-    uint32_t log_tl = 4;
-    while (log_tl < 8 && (double)(1u << log_tl) < 1.25 * (double)max_entries / (double)n_keys) log_tl++;
-    const uint64_t max_tasks = (uint64_t)n_keys + (max_entries >> log_tl) + 1;
+    // runs of L = 2^log_tl entries; smaller L when the problem is small, to keep the SMs busy
+    void *d_tcount, *d_toff, *d_partials, *d_big;
+    uint32_t log_tl = 6;
+    while (log_tl > 3 && (max_entries >> log_tl) < 65536) log_tl--;
+    const uint64_t max_runs = (max_entries >> log_tl) + 1;
+    const uint64_t max_segs = (uint64_t)n_keys + max_runs + 1;
     B200ZK_TRY(scratch(ctx, "msm_tcount", ((size_t)n_keys + 1) * 4, &d_tcount, slot));
     B200ZK_TRY(scratch(ctx, "msm_toff", ((size_t)n_keys + 1) * 4, &d_toff, slot));
-    B200ZK_TRY(scratch(ctx, "msm_tasks", (size_t)max_tasks * 4, &d_tasks, slot));
-    B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)(max_entries >> log_tl) / FOLD_SMALL_MAX + 8) * 4, &d_big, slot));
+    B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)max_runs / FOLD_SMALL_MAX + 8) * 4, &d_big, slot));
     {
         ProfScope ps(ctx, "msm_tasks", st);
-        msm_task_counts<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_offsets, n_keys, log_tl,
-                                                                      (uint32_t*)d_tcount);
-        B200ZK_TRY(check_launch(ctx, "msm_task_counts"));
+        msm_seg_counts<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_offsets, n_keys, log_tl,
+                                                            (uint32_t*)d_tcount);
+        B200ZK_TRY(check_launch(ctx, "msm_seg_counts"));
         B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
-        msm_task_list<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_toff, n_keys,
-                                                                    (uint32_t*)d_tasks);
-        B200ZK_TRY(check_launch(ctx, "msm_task_list"));
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, st));
         if (ctx->prof_enabled) {  // work counters for the roofline (costs a host sync: profiling runs only)
             uint32_t n_entries = 0;
@@ -501,15 +523,14 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         }
     }
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_partials_g1" : "msm_partials_g2",
-                       ((size_t)max_tasks + 1) * sizeof(XYZZ<F>), &d_partials, slot));
+                       ((size_t)max_segs + 1) * sizeof(XYZZ<F>), &d_partials, slot));
     uint32_t* big_count = (uint32_t*)d_big;
     uint32_t* big_list = (uint32_t*)d_big + 1;
     {
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2", st);
-        msm_accumulate<F><<<div_up(max_tasks, 128), 128, 0, st>>>(
+        msm_accumulate<F><<<div_up(max_runs, 128), 128, 0, st>>>(
             (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
-            (const uint32_t*)d_toff, (const uint32_t*)d_tasks, n_keys, log_tl, (XYZZ<F>*)d_buckets,
-            (XYZZ<F>*)d_partials);
+            (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
     }
     {
