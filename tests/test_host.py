@@ -1,0 +1,185 @@
+"""CPU-side checks of the product's host code (no GPU, no compute through the C ABI):
+  * libb200zk.so loads and exports every symbol include/b200zk.h declares; b200zk_init fails
+    loudly without a device (there is no CPU fallback);
+  * the host-only entry points (R1CS of the update-note relation, Poseidon parameter generation)
+    agree with the Python oracle;
+  * the portable (host) instantiation of csrc/field.cuh + ec.cuh -- the same limb algorithms and EC
+    formulas the kernels compile -- agrees with the Python oracle (tests/host/hostcheck.cpp)."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle.pyref import bls12_381 as bls, poseidon as pos, relations as rel
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R, P = bls.R, bls.P
+
+
+@pytest.fixture(scope="module")
+def z(built):
+    import zk_apps_b200 as z
+    return z
+
+
+@pytest.fixture(scope="module")
+def hc(built):
+    L = C.CDLL(os.path.join(ROOT, "tests", "host", "libhostcheck.so"))
+    vp = C.c_void_p
+    L.hc_field_op.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_size_t]
+    L.hc_msm_naive.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
+    L.hc_madd_chain.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ----------------------------------------------------------------------------- the C ABI
+def test_abi_exports_every_declared_symbol(z):
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200zk_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 40
+    lib = C.CDLL(z.lib_path())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in include/b200zk.h but not exported: %s" % missing
+
+
+def test_python_binding_covers_the_header(z):
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(b200zk_[a-z0-9_]+)\s*\(", hdr))
+    L = z.lib()
+    unbound = [n for n in names if getattr(L, n).argtypes is None]
+    assert not unbound, "no ctypes signature for: %s" % unbound
+
+
+def test_no_device_means_error_not_fallback(z):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    assert z.lib().b200zk_init(0, C.byref(h)) == -5          # B200ZK_ERR_NO_DEVICE
+    with pytest.raises(z.B200zkError):
+        z.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under zk-apps_b200/ may import or link it."""
+    pkg = os.path.join(ROOT, "zk-apps_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f == "build.py":          # build() also compiles the checker; building it is not using it
+                continue
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src and '#include "../../oracle' not in src, f
+
+
+# ----------------------------------------------------------------------------- host-only entry points
+@pytest.mark.parametrize("kind", [rel.DEPOSIT, rel.WITHDRAW])
+def test_update_note_r1cs_matches_oracle(z, kind):
+    """b200zk_update_note_r1cs (host_r1cs.hpp) vs the oracle's synthesis of update_note.rs:106-149."""
+    cs = rel.synthesize_update_note(rel.make_witness(4, kind))
+    r = z.UpdateNoteRelation(kind, rel.TREE_HEIGHT)
+    assert (r.num_constraints, r.num_inputs, r.num_variables) == (cs.num_constraints, cs.num_inputs, cs.num_variables)
+    for which, M in enumerate(cs.matrices()):
+        rp, cols, vals = r.matrix(which)
+        assert int(rp[-1]) == sum(len(row) for row in M) == r.nnz[which]
+        vals = bytes(vals)
+        k = 0
+        for i, row in enumerate(M):
+            assert int(rp[i]) == k
+            got = {int(cols[k + j]): bls.fr_from_mont_bytes(vals[32 * (k + j):32 * (k + j + 1)]) for j in range(len(row))}
+            want = {c: v % R for c, v in (row.items() if isinstance(row, dict) else row)}
+            assert got == want, (which, i)
+            k += len(row)
+    r.free()
+
+
+def test_update_note_r1cs_other_heights(z):
+    for h in (1, 4, 16):
+        r = z.UpdateNoteRelation(rel.WITHDRAW, h)
+        cs = rel.synthesize_update_note(rel.make_witness(1, rel.WITHDRAW, h), h)
+        assert (r.num_constraints, r.num_variables) == (cs.num_constraints, cs.num_variables)
+        r.free()
+
+
+def test_poseidon_constants_match_oracle(z):
+    rc, mds = z.poseidon_constants()
+    want_rc, want_mds = pos.constants()
+    assert util.fr_from_mont_array(rc) == [v for row in want_rc for v in row]
+    assert util.fr_from_mont_array(mds) == [v for row in want_mds for v in row]
+
+
+# ----------------------------------------------------------------------------- portable field / EC path
+@pytest.mark.parametrize("field", [0, 1, 2])
+def test_host_field_ops(hc, field):
+    rnd = random.Random(field)
+    mod, size = (R, 32) if field == 0 else (P, 48)
+    n = 200
+    def enc(vals):
+        if field == 0:
+            return np.frombuffer(b"".join(bls.fr_to_mont_bytes(v) for v in vals), dtype=np.uint8).copy()
+        if field == 1:
+            return np.frombuffer(b"".join(bls.fq_to_mont_bytes(v) for v in vals), dtype=np.uint8).copy()
+        return np.frombuffer(b"".join(bls.fq_to_mont_bytes(v[0]) + bls.fq_to_mont_bytes(v[1]) for v in vals), dtype=np.uint8).copy()
+    if field < 2:
+        A = [rnd.randrange(mod) for _ in range(n)] + [0, 1, mod - 1, mod - 1]
+        B = [rnd.randrange(mod) for _ in range(n)] + [mod - 1, mod - 1, mod - 1, 1]
+        ops = {0: lambda x, y: (x + y) % mod, 1: lambda x, y: (x - y) % mod, 2: lambda x, y: x * y % mod,
+               3: lambda x, y: x * x % mod, 4: lambda x, y: pow(x, -1, mod) if x else 0}
+    else:
+        A = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(n)] + [(0, 0), (1, 0), (0, 1), (P - 1, P - 1)]
+        B = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(n)] + [(P - 1, 1), (P - 1, P - 1), (0, P - 1), (P - 1, P - 1)]
+        ops = {0: bls.fq2_add, 1: bls.fq2_sub, 2: bls.fq2_mul, 3: lambda x, y: bls.fq2_sqr(x),
+               4: lambda x, y: bls.fq2_inv(x) if not bls.fq2_is_zero(x) else (0, 0)}
+    a, b = enc(A), enc(B)
+    for op, fn in ops.items():
+        out = np.zeros_like(a)
+        hc.hc_field_op(field, op, _p(a), _p(b), _p(out), len(A))
+        assert bytes(out) == bytes(enc([fn(x, y) for x, y in zip(A, B)])), (field, op)
+
+
+def test_host_mont_conversion(hc):
+    vals = [0, 1, 7, R - 1, 1 << 200]
+    canon = np.frombuffer(b"".join(bls.int_to_le(v, 32) for v in vals), dtype=np.uint8).copy()
+    out = np.zeros_like(canon)
+    hc.hc_field_op(0, 5, _p(canon), None, _p(out), len(vals))
+    assert bytes(out) == b"".join(bls.fr_to_mont_bytes(v) for v in vals)
+    back = np.zeros_like(canon)
+    hc.hc_field_op(0, 6, _p(out), None, _p(back), len(vals))
+    assert bytes(back) == bytes(canon)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_host_madd_special_cases(hc, group):
+    """XYZZ += affine through every branch: first add, doubling (P + P), cancellation (P - P), infinity operand."""
+    cv, enc, dec = (bls.G1, util.g1_array, util.g1_list) if group == 1 else (bls.G2, util.g2_array, util.g2_list)
+    g = cv.gen
+    p3, p5 = cv.mul(g, 3), cv.mul(g, 5)
+    cases = [([p3, p3], [0, 0], 6), ([p3, p3], [0, 1], 0), ([p3, p5, p3, None, p5], [0, 0, 1, 0, 0], 10),
+             ([None, p5], [0, 1], -5), ([p3, p3, p3, p3], [0, 0, 0, 0], 12), ([p5, p3, p3], [1, 0, 0], 1)]
+    for pts, neg, k in cases:
+        out = np.zeros(96 * group, dtype=np.uint8)
+        hc.hc_madd_chain(group, _p(enc(pts)), _p(np.array(neg, dtype=np.uint8)), len(pts), _p(out))
+        want = None if k == 0 else cv.mul(g, k % R)
+        assert dec(out)[0] == want, (pts, neg, k)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_host_scalar_mul_and_sum(hc, group):
+    cv, enc, dec = (bls.G1, util.g1_array, util.g1_list) if group == 1 else (bls.G2, util.g2_array, util.g2_list)
+    ks = [1, 2, 3, 4]
+    bases = [cv.mul(cv.gen, k) for k in ks]
+    for scalars, want in (([1, 2, 3, 4], 30), ([R - 1, 1, 0, 2], 9)):
+        out = np.zeros(96 * group, dtype=np.uint8)
+        hc.hc_msm_naive(group, _p(enc(bases)), _p(util.scalars_array(scalars)), 4, _p(out))
+        assert dec(out)[0] == cv.mul(cv.gen, want)
