@@ -294,6 +294,18 @@ def run_b200(args):
     buckets_g1 = ctx.stat_get("msm_buckets_g1")
     ctx.prof_enable(False)
     ctx.set_option("concurrency", 1)
+    if args.timeline and rank == 0:
+        # one step with concurrency ON and every kernel family bracketed: shows the overlap of the streams
+        ctx.prof_enable(True); ctx.prof_reset()
+        step_resident(0)
+        rows = ctx.prof_timeline()
+        ctx.prof_enable(False)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", args.timeline), "w") as f:
+            f.write("# one %d-proof step, concurrency on: kernel-family brackets, ms from the first bracket; @N = stream "
+                    "(0 main, 1-4 aux, 9 fin)\n" % B)
+            for name, a, b in sorted(rows, key=lambda r: r[1]):
+                f.write("%-28s %9.3f %9.3f  (%7.3f)\n" % (name, a, b, b - a))
     # ---- end-to-end leg (host buffers through the user-facing call)
     for i in range(2):
         step_e2e(i)
@@ -375,6 +387,7 @@ def main():
     ap.add_argument("--cpu-proofs", type=int, default=4, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--timeline", default="", help="write a per-kernel timeline of one concurrent step to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

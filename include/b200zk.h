@@ -76,6 +76,9 @@ int b200zk_prof_enable(b200zk_ctx* ctx, int on);
 int b200zk_prof_reset(b200zk_ctx* ctx);
 int b200zk_prof_get(b200zk_ctx* ctx, const char* name, double* ms, long* launches);
 int b200zk_prof_names(b200zk_ctx* ctx, char* buf, size_t buflen);   /* comma-separated */
+/* one line "name start_ms end_ms" per bracket since the last reset, offsets from the first bracket: shows
+ * how the streams of a proof batch overlap (valid when all brackets were resolved by one call). */
+int b200zk_prof_timeline(b200zk_ctx* ctx, char* buf, size_t buflen);
 long b200zk_launch_count(b200zk_ctx* ctx);
 /* work counters accumulated by the kernels' host wrappers, for roofline arithmetic:
  * "msm_entries_g1"/"msm_entries_g2" = mixed additions issued by msm_accumulate, "msm_buckets_g1/2". */
@@ -132,6 +135,17 @@ void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* h);
 int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars,
                         int scalars_on_device, size_t n, size_t batch, uint8_t* out_affine,
                         uint8_t* out_is_inf);
+
+/* ---- multi-GPU building blocks: a large MSM is split by point range, one
+ * rank per GPU; every rank computes the MSM of its slice with b200zk_msm_resident_device, which leaves
+ * the affine partial in device memory (e.g. directly in this rank's slot of an NCCL all_gather
+ * buffer) and does NOT synchronise the host; after the all_gather b200zk_points_sum[_device] adds the
+ * n partials (curve addition is not an NCCL reduction op).  zk-apps_b200/sharded.py is the host side. */
+int b200zk_msm_resident_device(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars, int scalars_on_device,
+                               size_t n, size_t batch, void* d_out_affine);
+int b200zk_points_sum(b200zk_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out_affine,
+                      uint8_t* out_is_inf);
+int b200zk_points_sum_device(b200zk_ctx* ctx, int group, const void* d_points, size_t n, void* d_out_affine);
 
 /* ---- the shielder relation: ConstraintSynthesizer side (host only, no GPU needed) ---------------
  * R1CS of update_note_circuit (shielder/relations/src/relations/update_note.rs:106-149) with the

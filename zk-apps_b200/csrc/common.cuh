@@ -33,6 +33,9 @@ struct b200zk_ctx {
     static constexpr int AUX_STREAMS = 4;                  // slots 1..4: independent MSMs of one proof batch
     cudaStream_t aux[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t fin = nullptr, fin2 = nullptr;            // high priority: latency-bound proof assembly pieces
+    cudaEvent_t ev_fin2 = nullptr, ev_fork2 = nullptr;     // fin2 joined into main; fin_scalars done
+    cudaEvent_t ev_msm[3] = {nullptr, nullptr, nullptr};   // completion of the a / b_g1 / b_g2 MSMs
     bool concurrency = true;                               // b200zk_set_option("concurrency")
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
@@ -43,6 +46,8 @@ struct b200zk_ctx {
     std::map<std::string, b200zk::KernelTimer> prof;
     std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
     std::vector<cudaEvent_t> event_pool;
+    std::vector<std::string> timeline;                     // "name start_ms end_ms" per bracket (b200zk_prof_timeline)
+    float timeline_base = 0.f;
     long launches = 0;                                     // every kernel launch of this library
     std::map<std::string, double> stats;                   // work counters (b200zk_stat_get)
     void* poseidon_consts = nullptr;                       // device copy, see poseidon.cu
@@ -127,7 +132,12 @@ struct ProfScope {
     ~ProfScope() {
         if (ctx->prof_enabled) {
             cudaEventRecord(b, st);
-            ctx->prof_pending.emplace_back(name, a, b);
+            int slot = 0;  // which stream: 0 main, 1..4 aux, 9 fin (shown in the timeline, stripped for the sums)
+            for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++)
+                if (st == ctx->aux[i]) slot = i + 1;
+            if (st == ctx->fin) slot = 9;
+            if (st == ctx->fin2) slot = 8;
+            ctx->prof_pending.emplace_back(std::string(name) + "@" + std::to_string(slot), a, b);
         }
     }
 };

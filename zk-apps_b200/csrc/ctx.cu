@@ -1,4 +1,5 @@
 // Context, device memory helpers and profiling hooks of the C ABI (include/b200zk.h).
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -19,17 +20,38 @@ int b200zk_init(int device, b200zk_ctx** out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // Stream priorities order the work of a proof batch (numerically lower = more urgent): the assembly pieces
+    // (fin, fin2) first, then the main stream (witness -> H(x) pipeline -> h MSM), then the MSMs a > b_g1 > b_g2 > l,
+    // one level each.  Blocks of a more urgent stream are dispatched first, so the MSMs complete one after the
+    // other instead of all at the end: the latency-bound phases of one (fold, bucket reduction, the scalar
+    // multiplications its result feeds) hide under the bucket accumulation of the next.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    auto prio = [&](int level) { return std::min(prio_lo, prio_hi + level); };
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio(1)) != cudaSuccess) {
         delete ctx;
         return B200ZK_ERR_CUDA;
     }
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
-        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+        static const int level[b200zk_ctx::AUX_STREAMS] = {2, 3, 5, 4};  // slots 1..4 = a, b_g1, l, b_g2
+        if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, prio(level[i])) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
             delete ctx;
             return B200ZK_ERR_CUDA;
         }
     }
+    if (cudaStreamCreateWithPriority(&ctx->fin, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->fin2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fin2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return B200ZK_ERR_CUDA;
+    }
+    for (int i = 0; i < 3; i++)
+        if (cudaEventCreateWithFlags(&ctx->ev_msm[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return B200ZK_ERR_CUDA;
+        }
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return B200ZK_ERR_CUDA;
@@ -57,6 +79,12 @@ void b200zk_destroy(b200zk_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->fin) cudaStreamDestroy(ctx->fin);
+    if (ctx->fin2) cudaStreamDestroy(ctx->fin2);
+    if (ctx->ev_fin2) cudaEventDestroy(ctx->ev_fin2);
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    for (int i = 0; i < 3; i++)
+        if (ctx->ev_msm[i]) cudaEventDestroy(ctx->ev_msm[i]);
     for (auto& kv : ctx->scratch)
         if (kv.second.ptr) cudaFree(kv.second.ptr);
     for (auto& kv : ctx->tables)
@@ -112,12 +140,24 @@ void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 static void prof_resolve(b200zk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) cudaStreamSynchronize(ctx->aux[i]);
+    if (ctx->fin) cudaStreamSynchronize(ctx->fin);
+    if (ctx->fin2) cudaStreamSynchronize(ctx->fin2);
     for (auto& t : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)) == cudaSuccess) {
-            KernelTimer& k = ctx->prof[std::get<0>(t)];
+            const std::string& tagged = std::get<0>(t);
+            KernelTimer& k = ctx->prof[tagged.substr(0, tagged.find('@'))];
             k.ms += ms;
             k.launches++;
+            // timeline: offsets from the first bracket since the last reset (events on any stream share one clock)
+            float t0 = 0.f;
+            cudaEvent_t origin = std::get<1>(ctx->prof_pending.front());
+            if (ctx->timeline.size() < 4096 && cudaEventElapsedTime(&t0, origin, std::get<1>(t)) == cudaSuccess) {
+                char line[160];
+                snprintf(line, sizeof line, "%s %.4f %.4f\n", std::get<0>(t).c_str(), ctx->timeline_base + t0,
+                         ctx->timeline_base + t0 + ms);
+                ctx->timeline.push_back(line);
+            }
         }
         ctx->event_pool.push_back(std::get<1>(t));
         ctx->event_pool.push_back(std::get<2>(t));
@@ -132,9 +172,22 @@ int b200zk_prof_enable(b200zk_ctx* ctx, int on) {
     return B200ZK_OK;
 }
 
+int b200zk_prof_timeline(b200zk_ctx* ctx, char* buf, size_t buflen) {
+    if (!ctx || !buf || !buflen) return B200ZK_ERR_BAD_ARG;
+    prof_resolve(ctx);
+    std::string s;
+    for (auto& l : ctx->timeline) {
+        if (s.size() + l.size() + 1 >= buflen) break;
+        s += l;
+    }
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return B200ZK_OK;
+}
+
 int b200zk_prof_reset(b200zk_ctx* ctx) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
     prof_resolve(ctx);
+    ctx->timeline.clear();
     ctx->prof.clear();
     return B200ZK_OK;
 }

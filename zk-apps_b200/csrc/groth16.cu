@@ -32,6 +32,7 @@ struct b200zk_pk {
     G1Affine alpha_g1, beta_g1, delta_g1;
     G2Affine beta_g2, delta_g2;
     void* d_singles = nullptr;  // alpha_g1, beta_g1, delta_g1 (G1Affine x3) then beta_g2, delta_g2 (G2Affine x2)
+    void* d_delta_tab = nullptr;  // DeltaTable: 2^(8j) * delta for j < 32, G1 and G2 (fixed-base comb for r*delta, s*delta)
 };
 
 namespace {
@@ -86,48 +87,80 @@ struct Singles {
     G2Affine beta_g2, delta_g2;
 };
 
+struct DeltaTable {
+    G1XYZZ g1[32];
+    G2XYZZ g2[32];
+};
+
+// tab[j] = 2^(8j) * delta (one thread per group; runs once per key)
+__global__ void delta_table_kernel(const Singles* __restrict__ sg, DeltaTable* __restrict__ tab) {
+    if (threadIdx.x == 0) {
+        G1XYZZ p = G1XYZZ::from_affine(sg->delta_g1);
+        for (int j = 0; j < 32; j++) {
+            tab->g1[j] = p;
+            for (int d = 0; d < 8; d++) p = ec_dbl(p);
+        }
+    } else if (threadIdx.x == 32) {
+        G2XYZZ p = G2XYZZ::from_affine(sg->delta_g2);
+        for (int j = 0; j < 32; j++) {
+            tab->g2[j] = p;
+            for (int d = 0; d < 8; d++) p = ec_dbl(p);
+        }
+    }
+}
+
+// k * delta with the comb table: lane j multiplies byte j of k into tab[j] (8 double-and-adds), then the
+// 32 partial sums are added in a shared-memory tree.  ~21 sequential group operations instead of ~380.
+template <class F>
+__device__ __forceinline__ XYZZ<F> comb_mul(const XYZZ<F>* __restrict__ tab, const uint32_t* k, XYZZ<F>* sh) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t digit = (k[lane >> 2] >> (8 * (lane & 3))) & 0xff;
+    const XYZZ<F> base = tab[lane];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int bit = 7; bit >= 0; bit--) {
+        acc = ec_dbl(acc);
+        if ((digit >> bit) & 1) ec_add(acc, base);
+    }
+    sh[lane] = acc;
+    __syncwarp();
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+        if (lane < step) {
+            XYZZ<F> b = sh[lane + step];
+            ec_add(acc, b);
+            sh[lane] = acc;
+        }
+        __syncwarp();
+    }
+    return acc;  // valid in lane 0
+}
+
 __device__ __forceinline__ void load_k(const uint8_t* p, uint32_t* k) {
     const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
 #pragma unroll
     for (int i = 0; i < 8; i++) k[i] = q[i];
 }
 
-// phase 1: t = j * batch + b ; j = 0: r*delta1, 1: s*delta1, 2: s*delta2
-__global__ void __launch_bounds__(32) finalize_phase1(const Singles* __restrict__ sg, const uint8_t* __restrict__ r,
-                                                      const uint8_t* __restrict__ s, uint32_t batch,
-                                                      G1XYZZ* __restrict__ t_g1 /*[2][batch]*/,
-                                                      G2XYZZ* __restrict__ t_g2 /*[batch]*/) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * batch) return;
-    const uint32_t j = t / batch, b = t % batch;
-    uint32_t k[8];
-    load_k((j == 0 ? r : s) + (size_t)b * 32, k);
-    if (j < 2) t_g1[(size_t)j * batch + b] = ec_mul_scalar(G1XYZZ::from_affine(sg->delta_g1), k);
-    else t_g2[b] = ec_mul_scalar(G2XYZZ::from_affine(sg->delta_g2), k);
-}
-
-// msm_g1 layout: [4][batch] = a, b_g1, l, h ; phase 2: j = 0: s*A, 1: r*B1, 2: (r*s)*delta1
-__global__ void __launch_bounds__(32) finalize_phase2(const Singles* __restrict__ sg, const uint8_t* __restrict__ r,
-                                                      const uint8_t* __restrict__ s, uint32_t batch,
-                                                      const G1Affine* __restrict__ msm_g1,
-                                                      const G1XYZZ* __restrict__ t_g1, G1XYZZ* __restrict__ u_g1 /*[3][batch]*/) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * batch) return;
-    const uint32_t j = t / batch, b = t % batch;
+// The assembly is cut along its data dependencies so that every piece can run on the high-priority
+// `fin` stream as soon as its inputs exist, hidden under the bucket accumulation of the slower MSMs
+// (each piece is a handful of 255-bit scalar multiplications per proof: latency-bound, 4 warps).
+//
+// fin_scalars (needs r, s only): one warp per (j, proof); j = 0: r*delta1, 1: s*delta1, 2: s*delta2, 3: (r*s)*delta1
+__global__ void __launch_bounds__(32) fin_scalars(const DeltaTable* __restrict__ tab, const uint8_t* __restrict__ r,
+                                                  const uint8_t* __restrict__ s, uint32_t batch,
+                                                  G1XYZZ* __restrict__ t_g1 /*[2][batch]*/, G2XYZZ* __restrict__ t_g2 /*[batch]*/,
+                                                  G1XYZZ* __restrict__ u_g1 /*[3][batch], slot 2 written here*/) {
+    __shared__ G2XYZZ sh2[32];
+    G1XYZZ* sh1 = reinterpret_cast<G1XYZZ*>(sh2);
+    const uint32_t j = blockIdx.x / batch, b = blockIdx.x % batch;
     uint32_t kr[8], ks[8];
     load_k(r + (size_t)b * 32, kr);
     load_k(s + (size_t)b * 32, ks);
-    G1XYZZ res;
-    if (j == 0) {  // s * A,  A = alpha + msm_a + r*delta1
-        G1XYZZ A = t_g1[b];
-        ec_madd(A, sg->alpha_g1);
-        ec_madd(A, msm_g1[(size_t)0 * batch + b]);
-        res = ec_mul_scalar(A, ks);
-    } else if (j == 1) {  // r * B1,  B1 = beta1 + msm_b1 + s*delta1
-        G1XYZZ B1 = t_g1[(size_t)batch + b];
-        ec_madd(B1, sg->beta_g1);
-        ec_madd(B1, msm_g1[(size_t)1 * batch + b]);
-        res = ec_mul_scalar(B1, kr);
+    if (j < 2) {
+        G1XYZZ v = comb_mul<Fq>(tab->g1, j == 0 ? kr : ks, sh1);
+        if (threadIdx.x == 0) t_g1[(size_t)j * batch + b] = v;
+    } else if (j == 2) {
+        G2XYZZ v = comb_mul<Fq2>(tab->g2, ks, sh2);
+        if (threadIdx.x == 0) t_g2[b] = v;
     } else {  // (r*s mod r) * delta1
         Fr fr_r, fr_s;
 #pragma unroll
@@ -136,9 +169,26 @@ __global__ void __launch_bounds__(32) finalize_phase2(const Singles* __restrict_
             fr_s.v[i] = ks[i];
         }
         Fr rs = fp_from_mont(fp_mul(fp_to_mont(fr_r), fp_to_mont(fr_s)));
-        res = ec_mul_scalar(G1XYZZ::from_affine(sg->delta_g1), rs.v);
+        G1XYZZ v = comb_mul<Fq>(tab->g1, rs.v, sh1);
+        if (threadIdx.x == 0) u_g1[(size_t)2 * batch + b] = v;
     }
-    u_g1[(size_t)j * batch + b] = res;
+}
+
+// msm_g1 layout: [4][batch] = a, b_g1, l, h.
+// fin_g1_mul: which = 0 (needs msm a):   u_g1[0] = s * A,   A  = alpha + msm_a  + r*delta1
+//             which = 1 (needs msm b_g1): u_g1[1] = r * B1,  B1 = beta1 + msm_b1 + s*delta1
+__global__ void __launch_bounds__(32) fin_g1_mul(const Singles* __restrict__ sg, const uint8_t* __restrict__ r,
+                                                 const uint8_t* __restrict__ s, uint32_t batch, uint32_t which,
+                                                 const G1Affine* __restrict__ msm_g1, const G1XYZZ* __restrict__ t_g1,
+                                                 G1XYZZ* __restrict__ u_g1) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    uint32_t k[8];
+    load_k((which == 0 ? s : r) + (size_t)b * 32, k);
+    G1XYZZ P = t_g1[(size_t)which * batch + b];
+    ec_madd(P, which == 0 ? sg->alpha_g1 : sg->beta_g1);
+    ec_madd(P, msm_g1[(size_t)which * batch + b]);
+    u_g1[(size_t)which * batch + b] = ec_mul_scalar(P, k);
 }
 
 // canonical big-endian bytes of an Fq (48 B)
@@ -187,25 +237,24 @@ __device__ void compress_g2(const G2Affine& p, uint8_t* out) {
     out[0] |= 0x80 | (largest ? 0x20 : 0);
 }
 
-// phase 3: t = j * batch + b ; j = 0: A, 1: B (G2), 2: C -> affine + compressed bytes
-__global__ void __launch_bounds__(32) finalize_phase3(const Singles* __restrict__ sg, uint32_t batch,
-                                                      const G1Affine* __restrict__ msm_g1,
-                                                      const G2Affine* __restrict__ msm_g2,
-                                                      const G1XYZZ* __restrict__ t_g1, const G2XYZZ* __restrict__ t_g2,
-                                                      const G1XYZZ* __restrict__ u_g1, uint8_t* __restrict__ proofs,
-                                                      uint8_t* __restrict__ points /* may be null: 384 B per proof */) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * batch) return;
-    const uint32_t j = t / batch, b = t % batch;
+// fin_output: part 0: A (needs msm a), 1: B in G2 (needs msm b_g2), 2: C (needs everything) -> affine + compressed bytes
+__global__ void __launch_bounds__(32) fin_output(const Singles* __restrict__ sg, uint32_t batch, uint32_t part,
+                                                 const G1Affine* __restrict__ msm_g1,
+                                                 const G2Affine* __restrict__ msm_g2,
+                                                 const G1XYZZ* __restrict__ t_g1, const G2XYZZ* __restrict__ t_g2,
+                                                 const G1XYZZ* __restrict__ u_g1, uint8_t* __restrict__ proofs,
+                                                 uint8_t* __restrict__ points /* may be null: 384 B per proof */) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
     uint8_t* out = proofs + (size_t)b * 192;
-    if (j == 0) {
+    if (part == 0) {
         G1XYZZ A = t_g1[b];
         ec_madd(A, sg->alpha_g1);
         ec_madd(A, msm_g1[(size_t)0 * batch + b]);
         G1Affine a = ec_to_affine(A);
         compress_g1(a, out);
         if (points) memcpy(points + (size_t)b * 384, &a, 96);
-    } else if (j == 1) {
+    } else if (part == 1) {
         G2XYZZ B = t_g2[b];
         ec_madd(B, sg->beta_g2);
         ec_madd(B, msm_g2[b]);
@@ -253,8 +302,12 @@ void free_pk(b200zk_pk* pk) {
         if (m.vals) cudaFree(m.vals);
     }
     for (b200zk_bases* h : {&pk->a_query, &pk->b_g1_query, &pk->b_g2_query, &pk->l_query, &pk->h_query})
+    {
         if (h->d_points) cudaFree(h->d_points);
+        if (h->d_skip) cudaFree(h->d_skip);
+    }
     if (pk->d_singles) cudaFree(pk->d_singles);
+    if (pk->d_delta_tab) cudaFree(pk->d_delta_tab);
     delete pk;
 }
 
@@ -278,6 +331,10 @@ int pk_singles(b200zk_ctx* ctx, b200zk_pk* pk) {
     Singles sg{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
     B200ZK_CUDA(ctx, cudaMalloc(&pk->d_singles, sizeof(Singles)));
     B200ZK_CUDA(ctx, cudaMemcpy(pk->d_singles, &sg, sizeof(sg), cudaMemcpyHostToDevice));
+    B200ZK_CUDA(ctx, cudaMalloc(&pk->d_delta_tab, sizeof(DeltaTable)));
+    delta_table_kernel<<<1, 64, 0, ctx->stream>>>((const Singles*)pk->d_singles, (DeltaTable*)pk->d_delta_tab);
+    B200ZK_TRY(check_launch(ctx, "delta_table_kernel"));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }
 
@@ -291,9 +348,37 @@ Fr fr_from_le(const uint8_t* p) {  // canonical LE -> Montgomery (host)
 
 namespace b200zk {
 
-// d_z: batch * num_vars Fr (Montgomery).  r, s: batch * 32 B canonical, host.
-int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, const uint8_t* r,
-                         const uint8_t* s, uint8_t* proofs_out, uint8_t* points_out) {
+// Everything that needs only (r, s): upload them and start the delta multiples on the `fin` stream.  Called
+// before witness generation by the user-facing path, so this latency-bound piece hides under it.
+int groth16_prove_begin(b200zk_ctx* ctx, const b200zk_pk* pk, size_t batch, const uint8_t* r, const uint8_t* s) {
+    const size_t B = batch;
+    void *d_rs, *d_t1, *d_t2, *d_u1;
+    B200ZK_TRY(scratch(ctx, "g16_rs", 2 * B * 32, &d_rs));
+    B200ZK_TRY(scratch(ctx, "g16_t1", 2 * B * sizeof(G1XYZZ), &d_t1));
+    B200ZK_TRY(scratch(ctx, "g16_t2", B * sizeof(G2XYZZ), &d_t2));
+    B200ZK_TRY(scratch(ctx, "g16_u1", 3 * B * sizeof(G1XYZZ), &d_u1));
+    uint8_t* d_r = (uint8_t*)d_rs;
+    uint8_t* d_s = d_r + B * 32;
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_r, r, B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_s, s, B * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const cudaStream_t fin = ctx->concurrency ? ctx->fin : ctx->stream;
+    if (ctx->concurrency) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(fin, ctx->ev_fork, 0));
+    }
+    {
+        ProfScope ps(ctx, "finalize", fin);
+        fin_scalars<<<(unsigned)(4 * B), 32, 0, fin>>>((const DeltaTable*)pk->d_delta_tab, d_r, d_s, (uint32_t)B,
+                                                       (G1XYZZ*)d_t1, (G2XYZZ*)d_t2, (G1XYZZ*)d_u1);
+        B200ZK_TRY(check_launch(ctx, "fin_scalars"));
+    }
+    if (ctx->concurrency) B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, fin));
+    return B200ZK_OK;
+}
+
+// d_z: batch * num_vars Fr (Montgomery).  groth16_prove_begin must have been called for this batch.
+int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, uint8_t* proofs_out,
+                         uint8_t* points_out) {
     const uint32_t n = 1u << pk->log_n, nv = pk->num_inputs + pk->num_aux;
     const size_t B = batch;
     void *d_abc, *d_rs, *d_msm1, *d_msm2, *d_t1, *d_t2, *d_u1, *d_proofs, *d_points = nullptr;
@@ -308,24 +393,56 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
     if (points_out) B200ZK_TRY(scratch(ctx, "g16_points", B * 384, &d_points));
     uint8_t* d_r = (uint8_t*)d_rs;
     uint8_t* d_s = d_r + B * 32;
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_r, r, B * 32, cudaMemcpyHostToDevice, ctx->stream));
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(d_s, s, B * 32, cudaMemcpyHostToDevice, ctx->stream));
     const Singles* sg = (const Singles*)pk->d_singles;
     G1Affine* m1 = (G1Affine*)d_msm1;
     const uint32_t* zs = (const uint32_t*)d_z;
     // ---- the four MSMs that only need z run on auxiliary streams, concurrently with H(x) below:
-    //      their latency-bound tails (bucket reduction) hide behind each other's bucket accumulation
-    if (ctx->concurrency) {
+    //      their latency-bound tails (bucket reduction) hide behind each other's bucket accumulation.
+    //      The proof assembly runs piecewise on the high-priority `fin` stream as its inputs appear.
+    const bool cc = ctx->concurrency;
+    const cudaStream_t fin = cc ? ctx->fin : ctx->stream;
+    const unsigned gb = div_up(B, 32);
+    if (cc) {
         B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[i], ctx->ev_fork, 0));
     }
+    const cudaStream_t fin2 = cc ? ctx->fin2 : ctx->stream;
+    auto wait_msm = [&](cudaStream_t who, int slot, int ev) -> int {  // `who` waits for the MSM that just went to `slot`
+        if (cc) {
+            B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_msm[ev], slot_stream(ctx, slot)));
+            B200ZK_CUDA(ctx, cudaStreamWaitEvent(who, ctx->ev_msm[ev], 0));
+        }
+        return B200ZK_OK;
+    };
     B200ZK_TRY(msm_device<Fq>(ctx, &pk->a_query, zs, nv, nv, B, true, m1 + 0 * B, 1));
-    B200ZK_TRY(msm_device<Fq2>(ctx, &pk->b_g2_query, zs, nv, nv, B, true, (G2Affine*)d_msm2, 4));
+    B200ZK_TRY(wait_msm(fin, 1, 0));
+    {   // fin: s*A, then the bytes of A
+        ProfScope ps(ctx, "finalize", fin);
+        fin_g1_mul<<<gb, 32, 0, fin>>>(sg, d_r, d_s, (uint32_t)B, 0, m1, (const G1XYZZ*)d_t1, (G1XYZZ*)d_u1);
+        B200ZK_TRY(check_launch(ctx, "fin_g1_mul"));
+        fin_output<<<gb, 32, 0, fin>>>(sg, (uint32_t)B, 0, m1, (const G2Affine*)d_msm2, (const G1XYZZ*)d_t1,
+                                       (const G2XYZZ*)d_t2, (const G1XYZZ*)d_u1, (uint8_t*)d_proofs, (uint8_t*)d_points);
+        B200ZK_TRY(check_launch(ctx, "fin_output"));
+    }
     B200ZK_TRY(msm_device<Fq>(ctx, &pk->b_g1_query, zs, nv, nv, B, true, m1 + 1 * B, 2));
+    if (cc) {  // fin2 starts after fin_scalars (first thing on fin) ...
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(fin2, ctx->ev_fork2, 0));
+    }
+    B200ZK_TRY(wait_msm(fin2, 2, 1));  // ... and after the b_g1 MSM
+    {   // fin2: r*B1, concurrently with s*A
+        ProfScope ps(ctx, "finalize", fin2);
+        fin_g1_mul<<<gb, 32, 0, fin2>>>(sg, d_r, d_s, (uint32_t)B, 1, m1, (const G1XYZZ*)d_t1, (G1XYZZ*)d_u1);
+        B200ZK_TRY(check_launch(ctx, "fin_g1_mul"));
+    }
+    B200ZK_TRY(msm_device<Fq2>(ctx, &pk->b_g2_query, zs, nv, nv, B, true, (G2Affine*)d_msm2, 4));
+    B200ZK_TRY(wait_msm(fin2, 4, 2));
+    {   // fin2: the bytes of B
+        ProfScope ps(ctx, "finalize", fin2);
+        fin_output<<<gb, 32, 0, fin2>>>(sg, (uint32_t)B, 1, m1, (const G2Affine*)d_msm2, (const G1XYZZ*)d_t1,
+                                        (const G2XYZZ*)d_t2, (const G1XYZZ*)d_u1, (uint8_t*)d_proofs, (uint8_t*)d_points);
+        B200ZK_TRY(check_launch(ctx, "fin_output"));
+    }
     B200ZK_TRY(msm_device<Fq>(ctx, &pk->l_query, zs + (size_t)pk->num_inputs * 8, pk->num_aux, nv, B, true, m1 + 2 * B, 3));
-    // scalar multiples of delta do not depend on the witness
-    finalize_phase1<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, d_r, d_s, (uint32_t)B, (G1XYZZ*)d_t1, (G2XYZZ*)d_t2);
-    B200ZK_TRY(check_launch(ctx, "finalize_phase1"));
 
     // ---- H(x) = (A*B - C) / Z
     Fr* abc = (Fr*)d_abc;
@@ -351,24 +468,22 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
     }
     B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, true, &g, B));
     B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B, 0));
-    if (ctx->concurrency) {
-        for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
-            B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->aux[i]));
-            B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
-        }
+    if (cc) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[2], ctx->aux[2]));  // slot 3: l
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[2], 0));
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], fin));          // fin has waited for a
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fin2, fin2));            // fin2 has waited for b_g1 and b_g2
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_fin2, 0));
     }
 
-    // ---- assembly + compression
+    // ---- C = s*A + r*B1 - rs*delta1 + l + h, and compression
     {
         ProfScope ps(ctx, "finalize");
-        finalize_phase2<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, d_r, d_s, (uint32_t)B, m1, (const G1XYZZ*)d_t1,
-                                                                   (G1XYZZ*)d_u1);
-        B200ZK_TRY(check_launch(ctx, "finalize_phase2"));
-        finalize_phase3<<<div_up(3 * B, 32), 32, 0, ctx->stream>>>(sg, (uint32_t)B, m1, (const G2Affine*)d_msm2,
-                                                                   (const G1XYZZ*)d_t1, (const G2XYZZ*)d_t2,
-                                                                   (const G1XYZZ*)d_u1, (uint8_t*)d_proofs,
-                                                                   (uint8_t*)d_points);
-        B200ZK_TRY(check_launch(ctx, "finalize_phase3"));
+        fin_output<<<gb, 32, 0, ctx->stream>>>(sg, (uint32_t)B, 2, m1, (const G2Affine*)d_msm2, (const G1XYZZ*)d_t1,
+                                               (const G2XYZZ*)d_t2, (const G1XYZZ*)d_u1, (uint8_t*)d_proofs,
+                                               (uint8_t*)d_points);
+        B200ZK_TRY(check_launch(ctx, "fin_output"));
     }
     B200ZK_CUDA(ctx, cudaMemcpyAsync(proofs_out, d_proofs, B * 192, cudaMemcpyDeviceToHost, ctx->stream));
     if (points_out) B200ZK_CUDA(ctx, cudaMemcpyAsync(points_out, d_points, B * 384, cudaMemcpyDeviceToHost, ctx->stream));
@@ -554,7 +669,8 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
         B200ZK_CUDA(ctx, cudaMemcpyAsync(d, assignments, batch * nv * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
         dz = (const Fr*)d;
     }
-    return groth16_prove_device(ctx, pk, dz, batch, r, s, proofs_out, points_out);
+    B200ZK_TRY(groth16_prove_begin(ctx, pk, batch, r, s));
+    return groth16_prove_device(ctx, pk, dz, batch, proofs_out, points_out);
 }
 
 static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, int inputs_on_device,
@@ -571,6 +687,7 @@ static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const ui
     B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
     if (!inputs_on_device)
         B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(groth16_prove_begin(ctx, pk, batch, r, s));
     B200ZK_TRY(update_note_witness_device(ctx, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
     std::vector<uint32_t> st(batch);
     B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -583,7 +700,7 @@ static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const ui
     }
     // like arkworks, an unsatisfied instance is an error, not a proof (SynthesisError::Unsatisfiable in debug builds)
     if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the update-note relation");
-    return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, r, s, proofs_out, nullptr);
+    return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, proofs_out, nullptr);
 }
 
 int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,

@@ -101,10 +101,11 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t idx,
 
 // scalars: batch rows of n scalars, row stride `stride` elements
 __global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
-                          uint32_t* counts) {
+                          const uint8_t* __restrict__ skip, uint32_t* counts) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     const size_t b = t / n, i = t % n;
+    if (skip && skip[i]) return;
     uint32_t k[8];
     load_scalar(scalars, b * stride + i, mont != 0, k);
     uint32_t carry = 0;
@@ -118,10 +119,11 @@ __global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size
 }
 
 __global__ void msm_scatter(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
-                            uint32_t* cursor, uint32_t* sorted) {
+                            const uint8_t* __restrict__ skip, uint32_t* cursor, uint32_t* sorted) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     const size_t b = t / n, i = t % n;
+    if (skip && skip[i]) return;
     uint32_t k[8];
     load_scalar(scalars, b * stride + i, mont != 0, k);
     uint32_t carry = 0;
@@ -435,9 +437,41 @@ __global__ void __launch_bounds__(64) msm_precompute_step(const Affine<F>* __res
 }
 
 template <class F>
+__global__ void mark_infinity(const Affine<F>* __restrict__ pts, size_t n, uint8_t* __restrict__ flags,
+                              unsigned long long* __restrict__ count) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool inf = load_affine(pts + i).is_inf();
+    flags[i] = inf ? 1 : 0;
+    if (inf) atomicAdd(count, 1ull);
+}
+
+template <class F>
 __global__ void apply_inf_flags(Affine<F>* pts, const uint8_t* flags, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n && flags[i]) pts[i] = Affine<F>::inf();
+}
+
+// out = sum of n affine points: lanes stride over the points, then a shared-memory tree (one warp).
+// Used to combine the per-GPU partial results of a sharded MSM.
+template <class F>
+__global__ void __launch_bounds__(32) points_sum_kernel(const Affine<F>* __restrict__ pts, uint32_t n,
+                                                        Affine<F>* __restrict__ out) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t lane = threadIdx.x;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = lane; i < n; i += 32) ec_madd(acc, load_affine(pts + i));
+    sh[lane] = acc;
+    __syncwarp();
+    for (uint32_t step = 16; step >= 1; step >>= 1) {
+        if (lane < step) {
+            XYZZ<F> b = sh[lane + step];
+            ec_add(acc, b);
+            sh[lane] = acc;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *out = ec_to_affine(acc);
 }
 
 int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, int slot, const uint32_t* d_in, size_t n,
@@ -489,12 +523,12 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
     {
         ProfScope ps(ctx, "msm_sort", st);
-        msm_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+        msm_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl, h->d_skip,
                                                                (uint32_t*)d_counts);
         B200ZK_TRY(check_launch(ctx, "msm_count"));
         B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_counts, n_keys, (uint32_t*)d_offsets));
         B200ZK_CUDA(ctx, cudaMemcpyAsync(d_cursor, d_offsets, (size_t)n_keys * 4, cudaMemcpyDeviceToDevice, st));
-        msm_scatter<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl,
+        msm_scatter<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl, h->d_skip,
                                                                  (uint32_t*)d_cursor, (uint32_t*)d_sorted);
         B200ZK_TRY(check_launch(ctx, "msm_scatter"));
     }
@@ -514,7 +548,7 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         B200ZK_TRY(check_launch(ctx, "msm_seg_counts"));
         B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_big, 0, 4, st));
-        if (ctx->prof_enabled) {  // work counters for the roofline (costs a host sync: profiling runs only)
+        if (ctx->prof_enabled && !ctx->concurrency) {  // work counters for the roofline (costs a host sync: serialised profiling runs only)
             uint32_t n_entries = 0;
             B200ZK_CUDA(ctx, cudaMemcpyAsync(&n_entries, (const uint32_t*)d_offsets + n_keys, 4, cudaMemcpyDeviceToHost, st));
             B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
@@ -598,6 +632,23 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
         apply_inf_flags<F><<<div_up(n, 256), 256, 0, ctx->stream>>>((Affine<F>*)h->d_points, (const uint8_t*)df, n);
         B200ZK_TRY(check_launch(ctx, "apply_inf_flags"));
     }
+    {   // bases at infinity are dropped at sort time instead of costing a (no-op) bucket addition each
+        void* dcount;
+        B200ZK_TRY(scratch(ctx, "msm_inf_count", 8, &dcount));
+        B200ZK_CUDA(ctx, cudaMemsetAsync(dcount, 0, 8, ctx->stream));
+        B200ZK_CUDA(ctx, cudaMalloc(&h->d_skip, n));
+        mark_infinity<F><<<div_up(n, 256), 256, 0, ctx->stream>>>((const Affine<F>*)h->d_points, n, h->d_skip,
+                                                                  (unsigned long long*)dcount);
+        B200ZK_TRY(check_launch(ctx, "mark_infinity"));
+        unsigned long long cnt = 0;
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(&cnt, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h->n_skip = (size_t)cnt;
+        if (cnt == 0) {
+            cudaFree(h->d_skip);
+            h->d_skip = nullptr;
+        }
+    }
     if (precompute) {
         Affine<F>* t = (Affine<F>*)h->d_points;
         for (uint32_t w = 1; w < pl.windows; w++) {
@@ -646,6 +697,7 @@ int msm_host_entry(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8
     }
     cudaStreamSynchronize(ctx->stream);
     if (h.d_points) cudaFree(h.d_points);
+    if (h.d_skip) cudaFree(h.d_skip);
     return rc;
 }
 
@@ -674,6 +726,7 @@ int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const 
                         : bases_build<Fq2>(ctx, h, (const Affine<Fq2>*)bases, false, inf_flags, n, precompute);
     if (rc != B200ZK_OK) {
         if (h->d_points) cudaFree(h->d_points);
+        if (h->d_skip) cudaFree(h->d_skip);
         delete h;
         return rc;
     }
@@ -692,6 +745,7 @@ int b200zk_bases_from_device(b200zk_ctx* ctx, int group, const void* d_points, s
                         : bases_build<Fq2>(ctx, h, (const Affine<Fq2>*)d_points, true, nullptr, n, precompute);
     if (rc != B200ZK_OK) {
         if (h->d_points) cudaFree(h->d_points);
+        if (h->d_skip) cudaFree(h->d_skip);
         delete h;
         return rc;
     }
@@ -706,6 +760,7 @@ void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* h) {
         cudaStreamSynchronize(ctx->stream);
     }
     if (h->d_points) cudaFree(h->d_points);
+    if (h->d_skip) cudaFree(h->d_skip);
     delete h;
 }
 
@@ -735,6 +790,54 @@ int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scal
             for (size_t i = 0; i < pt; i++) z = z && out_affine[b * pt + i] == 0;
             out_is_inf[b] = z ? 1 : 0;
         }
+    return B200ZK_OK;
+}
+
+int b200zk_msm_resident_device(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars, int scalars_on_device,
+                               size_t n, size_t batch, void* d_out_affine) {
+    if (!ctx || !h || !d_out_affine || (n && batch && !scalars)) return B200ZK_ERR_BAD_ARG;
+    if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
+    if (batch == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t* ds = (const uint32_t*)scalars;
+    if (!scalars_on_device) {
+        void* d;
+        B200ZK_TRY(scratch(ctx, "msm_scalars", std::max<size_t>(32, n * batch * 32), &d));
+        if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(d, scalars, n * batch * 32, cudaMemcpyHostToDevice, ctx->stream));
+        ds = (const uint32_t*)d;
+    }
+    if (h->group == 1) return msm_device<Fq>(ctx, h, ds, n, n, batch, false, (G1Affine*)d_out_affine);
+    return msm_device<Fq2>(ctx, h, ds, n, n, batch, false, (G2Affine*)d_out_affine);
+}
+
+int b200zk_points_sum_device(b200zk_ctx* ctx, int group, const void* d_points, size_t n, void* d_out_affine) {
+    if (!ctx || !d_out_affine || (n && !d_points)) return B200ZK_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+    if (n >= (1ull << 32)) return fail(ctx, B200ZK_ERR_BAD_LEN, "too many points");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (group == 1) points_sum_kernel<Fq><<<1, 32, 0, ctx->stream>>>((const G1Affine*)d_points, (uint32_t)n, (G1Affine*)d_out_affine);
+    else points_sum_kernel<Fq2><<<1, 32, 0, ctx->stream>>>((const G2Affine*)d_points, (uint32_t)n, (G2Affine*)d_out_affine);
+    return check_launch(ctx, "points_sum_kernel");
+}
+
+int b200zk_points_sum(b200zk_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out_affine,
+                      uint8_t* out_is_inf) {
+    if (!ctx || !out_affine || (n && !points)) return B200ZK_ERR_BAD_ARG;
+    if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pt = group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    void *d, *dout;
+    B200ZK_TRY(scratch(ctx, "psum_in", std::max<size_t>(pt, n * pt), &d));
+    B200ZK_TRY(scratch(ctx, "psum_out", pt, &dout));
+    if (n) B200ZK_CUDA(ctx, cudaMemcpyAsync(d, points, n * pt, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(b200zk_points_sum_device(ctx, group, d, n, dout));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine, dout, pt, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_is_inf) {
+        bool z = true;
+        for (size_t i = 0; i < pt; i++) z = z && out_affine[i] == 0;
+        *out_is_inf = z ? 1 : 0;
+    }
     return B200ZK_OK;
 }
 

@@ -10,6 +10,9 @@ struct b200zk_bases {
     void* d_points = nullptr;  // Affine<F>[n * (precomputed ? windows : 1)]
     int precomputed = 0;
     uint32_t c = 0, windows = 0;
+    uint8_t* d_skip = nullptr;  // n flags: base i is the point at infinity (its digits never enter a bucket);
+                                // null when no base is (proving-key b queries are ~30 % infinity)
+    size_t n_skip = 0;
 };
 
 struct b200zk_r1cs {

@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
             "b200zk_prof_reset": (i32, [vp]),
             "b200zk_prof_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
             "b200zk_prof_names": (i32, [vp, C.c_char_p, sz]),
+            "b200zk_prof_timeline": (i32, [vp, C.c_char_p, sz]),
             "b200zk_launch_count": (C.c_long, [vp]),
             "b200zk_dbg_field_op": (i32, [vp, i32, i32, vp, vp, vp, sz]),
             "b200zk_dbg_int_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
@@ -72,6 +73,9 @@ def lib() -> C.CDLL:
             "b200zk_bases_from_device": (i32, [vp, i32, vp, sz, i32, C.POINTER(vp)]),
             "b200zk_bases_free": (None, [vp, vp]),
             "b200zk_msm_resident": (i32, [vp, vp, vp, i32, sz, sz, vp, vp]),
+            "b200zk_msm_resident_device": (i32, [vp, vp, vp, i32, sz, sz, vp]),
+            "b200zk_points_sum": (i32, [vp, i32, vp, sz, vp, vp]),
+            "b200zk_points_sum_device": (i32, [vp, i32, vp, sz, vp]),
             "b200zk_update_note_r1cs": (i32, [i32, u32, C.POINTER(vp)]),
             "b200zk_r1cs_free": (None, [vp]),
             "b200zk_r1cs_shape": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -185,6 +189,16 @@ class Context:
         self.check(lib().b200zk_prof_names(self._h, buf, 4096))
         return [s for s in buf.value.decode().split(",") if s]
 
+    def prof_timeline(self):
+        """[(name, start_ms, end_ms)] of every profiled bracket since the last prof_reset."""
+        buf = C.create_string_buffer(1 << 20)
+        self.check(lib().b200zk_prof_timeline(self._h, buf, 1 << 20))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, a, b = line.rsplit(" ", 2)
+            rows.append((name, float(a), float(b)))
+        return rows
+
     def launch_count(self) -> int:
         return lib().b200zk_launch_count(self._h)
 
@@ -275,12 +289,34 @@ class VariableBaseMSM:
                                                      out.ctypes.data_as(C.c_void_p), inf.ctypes.data_as(C.c_void_p)))
             return out, inf
 
+        def msm_to_device(self, d_out: int, scalars=None, n: int | None = None, batch: int = 1,
+                          device_ptr: int | None = None):
+            """Same MSM, affine result(s) left at device address `d_out`; asynchronous on the ctx stream."""
+            if device_ptr is not None:
+                ps, on_dev = C.c_void_p(device_ptr), 1
+            else:
+                ps, ks = _buf(scalars)
+                on_dev = 0
+                if n is None:
+                    n = ks.nbytes // 32 // batch
+            self.ctx.check(lib().b200zk_msm_resident_device(self.ctx.handle, self._h, ps, on_dev, n, batch, C.c_void_p(d_out)))
+
         def free(self):
             if self._h:
                 lib().b200zk_bases_free(self.ctx.handle, self._h)
                 self._h = None
 
         __del__ = free
+
+
+def points_sum(ctx: Context, group: int, points) -> tuple:
+    """Sum of affine points (host buffer) -> (affine bytes, is_infinity)."""
+    pt = G1_BYTES if group == 1 else G2_BYTES
+    pp, kp = _buf(points)
+    out = np.zeros(pt, dtype=np.uint8)
+    inf = C.c_uint8()
+    ctx.check(lib().b200zk_points_sum(ctx.handle, group, pp, kp.nbytes // pt, out.ctypes.data_as(C.c_void_p), C.byref(inf)))
+    return out.tobytes(), bool(inf.value)
 
 
 class Radix2EvaluationDomain:
