@@ -257,8 +257,8 @@ __device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_
     else partials[s0 + (run - (offsets[key] >> log_tl))] = acc;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) msm_accumulate(const Affine<F>* __restrict__ bases,
+template <class F, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F>* __restrict__ bases,
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ soff, uint32_t n_keys,
@@ -368,46 +368,112 @@ __global__ void __launch_bounds__(32) msm_fold_big(const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------- bucket reduction
-// chunk t of bucket set s covers buckets [t*S, (t+1)*S): out = sum_j (t*S + j + 1) * B_j
+// Weighted bucket sum  W = sum_j (j+1) B_j  of one bucket set, organised for DEPTH, not only for work: this
+// phase has little arithmetic (2-3 additions per bucket) but sits at the tail of every MSM, where nothing
+// is left to overlap with.  One CTA per segment of up to RED_SEG buckets:
+//   thread t owns I consecutive buckets: running sums give R_t = sum B and w_t = sum (i+1) B      (2I adds deep)
+//   Hillis-Steele suffix scan of R_t over the CTA in shared memory: Inc_t = sum_{u >= t} R_u      (log T deep)
+//   v_t = w_t + I * Inc_t (t >= 1), tree sum of v_t                                              (log T deep)
+// since  sum_j (j+1) B_j = sum_t [ w_t + t I R_t ]  and  sum_t t R_t = sum_{t >= 1} Inc_t.
+// ~36 additions deep for 2048 buckets instead of ~95 for the chunked running-sum version it replaces.
+constexpr uint32_t RED_THREADS = 256, RED_SEG = 2048;
+
+// all threads of the CTA call this; results valid in thread 0
 template <class F>
-__global__ void __launch_bounds__(64) msm_chunk_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t nb,
-                                                       uint32_t log_s, uint32_t n_chunks_total,
-                                                       XYZZ<F>* __restrict__ out) {
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n_chunks_total) return;
-    const uint32_t S = 1u << log_s;
-    const uint32_t chunks_per_set = nb >> log_s;
-    const uint32_t set = id / chunks_per_set, t = id % chunks_per_set;
-    const XYZZ<F>* B = buckets + (size_t)set * nb + (size_t)t * S;
-    XYZZ<F> run = XYZZ<F>::inf(), sum = XYZZ<F>::inf();
-    for (int j = (int)S - 1; j >= 0; j--) {
-        XYZZ<F> b = B[j];
-        ec_add(run, b);
-        ec_add(sum, run);
+__device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m, XYZZ<F>* sh, XYZZ<F>& W_out,
+                                   XYZZ<F>& R_out) {
+    const uint32_t t = threadIdx.x, T = blockDim.x;
+    uint32_t log_i = 0;
+    while ((T << log_i) < m) log_i++;
+    const uint32_t I = 1u << log_i;
+    XYZZ<F> run = XYZZ<F>::inf(), w = XYZZ<F>::inf();
+    if (t * I < m) {
+        const XYZZ<F>* B = items + (size_t)t * I;
+        for (int i = (int)I - 1; i >= 0; i--) {
+            XYZZ<F> b = B[i];
+            ec_add(run, b);
+            ec_add(w, run);
+        }
     }
-    if (t) {
-        XYZZ<F> m = ec_mul_small(run, t << log_s);
-        ec_add(sum, m);
+    // inclusive suffix scan of `run`
+    XYZZ<F> x = run;
+    sh[t] = x;
+    __syncthreads();
+    const uint32_t active = (m + I - 1) >> log_i;  // threads holding data
+    for (uint32_t d = 1; d < active; d <<= 1) {
+        const bool has = t + d < active;
+        XYZZ<F> other;
+        if (has) other = sh[t + d];
+        __syncthreads();
+        if (has) {
+            ec_add(x, other);
+            sh[t] = x;
+        }
+        __syncthreads();
     }
-    out[id] = sum;
+    XYZZ<F> v = w;
+    if (t >= 1 && t < active) {
+        XYZZ<F> s = x;
+        for (uint32_t d = 0; d < log_i; d++) s = ec_dbl(s);
+        ec_add(v, s);
+    }
+    if (t == 0) R_out = x;
+    __syncthreads();
+    sh[t] = v;
+    __syncthreads();
+    for (uint32_t step = T >> 1; step >= 1; step >>= 1) {
+        if (t < step && t + step < active) {
+            XYZZ<F> b = sh[t + step];
+            ec_add(v, b);
+            sh[t] = v;
+        }
+        __syncthreads();
+    }
+    if (t == 0) W_out = v;
 }
 
-// out[g][i] = sum of in[g][i*R .. i*R+R) ; m_in values per group
+// segment g of set s covers buckets [g*seg, (g+1)*seg): W[s*segs+g] = sum_i (i+1) B_i, R[...] = sum_i B_i
 template <class F>
-__global__ void __launch_bounds__(64) msm_sum(const XYZZ<F>* __restrict__ in, uint32_t groups, uint32_t m_in,
-                                              uint32_t R, XYZZ<F>* __restrict__ out) {
-    const uint32_t m_out = (m_in + R - 1) / R;
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= groups * m_out) return;
-    const uint32_t g = id / m_out, i = id % m_out;
-    const XYZZ<F>* src = in + (size_t)g * m_in;
-    XYZZ<F> acc = XYZZ<F>::inf();
-    const uint32_t hi = min(m_in, (i + 1) * R);
-    for (uint32_t j = i * R; j < hi; j++) {
-        XYZZ<F> b = src[j];
-        ec_add(acc, b);
+__global__ void __launch_bounds__(RED_THREADS) msm_seg_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t seg,
+                                                              XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ R) {
+    extern __shared__ uint4 red_smem[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(red_smem);
+    XYZZ<F> w, r;
+    block_weighted_sum<F>(buckets + (size_t)blockIdx.x * seg, seg, sh, w, r);
+    if (threadIdx.x == 0) {
+        W[blockIdx.x] = w;
+        R[blockIdx.x] = r;
     }
-    out[id] = acc;
+}
+
+// one CTA per set: out = sum_g W_g + seg * sum_{g >= 1} g R_g   (segs <= RED_THREADS)
+template <class F>
+__global__ void __launch_bounds__(RED_THREADS) msm_seg_combine(const XYZZ<F>* __restrict__ W, const XYZZ<F>* __restrict__ R,
+                                                               uint32_t segs, uint32_t log_seg, XYZZ<F>* __restrict__ out) {
+    extern __shared__ uint4 red_smem[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(red_smem);
+    const uint32_t t = threadIdx.x;
+    const XYZZ<F>* Ws = W + (size_t)blockIdx.x * segs;
+    const XYZZ<F>* Rs = R + (size_t)blockIdx.x * segs;
+    XYZZ<F> hi, unused;
+    block_weighted_sum<F>(Rs + 1, segs - 1, sh, hi, unused);  // sum_{g>=1} g R_g (weights 1.. over R_1..)
+    __syncthreads();
+    XYZZ<F> v = t < segs ? Ws[t] : XYZZ<F>::inf();
+    sh[t] = v;
+    __syncthreads();
+    for (uint32_t step = blockDim.x >> 1; step >= 1; step >>= 1) {
+        if (t < step) {
+            XYZZ<F> b = sh[t + step];
+            ec_add(v, b);
+            sh[t] = v;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        for (uint32_t d = 0; d < log_seg; d++) hi = ec_dbl(hi);
+        ec_add(v, hi);
+        out[blockIdx.x] = v;
+    }
 }
 
 // window sums [batch][weff] -> affine result per msm
@@ -562,7 +628,11 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     uint32_t* big_list = (uint32_t*)d_big + 1;
     {
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2", st);
-        msm_accumulate<F><<<div_up(max_runs, 128), 128, 0, st>>>(
+        // resident CTAs per SM (register cap 65536 / (128 * blocks)); tunable for experiments
+        static const int occ_env = getenv("B200ZK_ACC_BLOCKS") ? atoi(getenv("B200ZK_ACC_BLOCKS")) : 0;
+        const int occ = occ_env ? occ_env : 2;  // measured: 3 gains 1.6 % alone but crowds out the concurrent tails
+        auto kern = occ >= 4 ? msm_accumulate<F, 4> : occ == 3 ? msm_accumulate<F, 3> : msm_accumulate<F, 2>;
+        kern<<<div_up(max_runs, 128), 128, 0, st>>>(
             (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
             (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
@@ -579,27 +649,30 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     }
     // bucket reduction
     const uint32_t sets = (uint32_t)batch * pl.weff;
-    uint32_t log_s = 5;
-    while ((1u << log_s) > pl.nb) log_s--;
-    const uint32_t chunks_per_set = pl.nb >> log_s;
-    const uint32_t n_chunks = sets * chunks_per_set;
-    B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)n_chunks * sizeof(XYZZ<F>), &d_red_a, slot));
-    B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)n_chunks / 8 + sets + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
+    const uint32_t seg = std::min(pl.nb, RED_SEG), segs = pl.nb / seg;
+    uint32_t log_seg = 0;
+    while ((1u << log_seg) < seg) log_seg++;
+    if (segs > RED_THREADS) return fail(ctx, B200ZK_ERR_BAD_ARG, "window too large for the bucket reduction");
+    const size_t red_smem = (size_t)RED_THREADS * sizeof(XYZZ<F>);
+    B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)sets * segs * 2 * sizeof(XYZZ<F>), &d_red_a, slot));
+    B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)sets + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
     {
         ProfScope ps(ctx, "msm_reduce", st);
-        msm_chunk_reduce<F><<<div_up(n_chunks, 64), 64, 0, st>>>((const XYZZ<F>*)d_buckets, pl.nb, log_s,
-                                                                           n_chunks, (XYZZ<F>*)d_red_a);
-        B200ZK_TRY(check_launch(ctx, "msm_chunk_reduce"));
-        uint32_t m = chunks_per_set;
-        XYZZ<F>* src = (XYZZ<F>*)d_red_a;
-        XYZZ<F>* dst = (XYZZ<F>*)d_red_b;
-        while (m > 1) {
-            const uint32_t R = 8;
-            const uint32_t m_out = (m + R - 1) / R;
-            msm_sum<F><<<div_up((size_t)sets * m_out, 64), 64, 0, st>>>(src, sets, m, R, dst);
-            B200ZK_TRY(check_launch(ctx, "msm_sum"));
-            std::swap(src, dst);
-            m = m_out;
+        static bool attr_done[2] = {false, false};
+        if (!attr_done[sizeof(F) == sizeof(Fq) ? 0 : 1]) {
+            B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_seg_reduce<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+            B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_seg_combine<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+            attr_done[sizeof(F) == sizeof(Fq) ? 0 : 1] = true;
+        }
+        XYZZ<F>* Wseg = (XYZZ<F>*)d_red_a;
+        XYZZ<F>* Rseg = Wseg + (size_t)sets * segs;
+        msm_seg_reduce<F><<<sets * segs, RED_THREADS, red_smem, st>>>((const XYZZ<F>*)d_buckets, seg, Wseg, Rseg);
+        B200ZK_TRY(check_launch(ctx, "msm_seg_reduce"));
+        XYZZ<F>* src = Wseg;
+        if (segs > 1) {
+            msm_seg_combine<F><<<sets, RED_THREADS, red_smem, st>>>(Wseg, Rseg, segs, log_seg, (XYZZ<F>*)d_red_b);
+            B200ZK_TRY(check_launch(ctx, "msm_seg_combine"));
+            src = (XYZZ<F>*)d_red_b;
         }
         msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(src, (uint32_t)batch, pl.weff, pl.c, d_out);
         B200ZK_TRY(check_launch(ctx, "msm_finish"));

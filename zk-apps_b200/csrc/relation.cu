@@ -5,8 +5,10 @@
 // merkle_proof.rs:38-61 (path walk), lib.rs:17-26 (Poseidon parameters); the permutation itself
 // lives in the un-vendored halo2-base 0.4.1 (PARITY UNPINNED, see oracle/pyref/poseidon.py).
 //
-// Mapping: one proof per 8-lane group (4 proofs per warp).  Lanes 0..4 of a group each hold one
-// word of the Poseidon state; the 5x5 MDS row products exchange state words with warp shuffles.
+// Mapping.  Witness generator: two warps per proof (the Merkle-path chain on one, the note/account
+// hashes and the balance update on the other), each running a warp-wide Poseidon laid out for depth
+// (25 lanes = 5x5 MDS products, see poseidon_permute_w).  Batched hashing (poseidon_hash_batch): one
+// hash per 8-lane group, 5 lanes hold the state, laid out for throughput.
 // Every S-box writes its (x^2, x^4, x^5) straight into the proof's assignment vector z, in the
 // order host_r1cs.hpp allocates them, so the R1CS witness is a by-product of hashing.
 #include <cstring>
@@ -98,127 +100,180 @@ __device__ __forceinline__ bool fits_bits128(const Fr& canon) {
     return (canon.v[4] | canon.v[5] | canon.v[6] | canon.v[7]) == 0;
 }
 
+// ---- warp-wide Poseidon for the witness generator -------------------------------------------------
+// Witness generation is pure latency (a few hundred warps in flight, nothing to overlap with: every MSM
+// waits for z), so the permutation is laid out for depth.  Lane 5*l + j (l, j < 5) holds a copy of state
+// word j: every lane applies the S-box to its own copy (redundantly across l), multiplies by M[l][j], and
+// the row sums  s'_j = sum_k M[j][k] s_k  are gathered with shuffles from lanes 5*j + k -- the gather also
+// transposes, so each lane ends up with its own word again.  4 multiplications deep per round instead of 8.
+__device__ __forceinline__ Fr warp_get(const Fr& v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src);
+    return r;
+}
+
+__device__ void poseidon_permute_w(Fr& s, int lane, const PoseidonConsts* pc, Fr* trace) {
+    const int half = host::POSEIDON_RF / 2;
+    const int j = lane % 5, l = lane < 25 ? lane / 5 : 0;  // lanes 25..31 shadow row 0; nobody reads them
+    int sbox = 0;
+    for (int rnd = 0; rnd < host::POSEIDON_ROUNDS; rnd++) {
+        const bool full = rnd < half || rnd >= half + host::POSEIDON_RP;
+        s = fp_add(s, ld_fr(&pc->rc[rnd][j]));
+        if (full || j == 0) {
+            Fr x2 = fp_sqr(s);
+            Fr x4 = fp_sqr(x2);
+            Fr x5 = fp_mul(x4, s);
+            if (trace && lane < 5) {
+                Fr* t = trace + (size_t)(sbox + (full ? j : 0)) * 3;
+                st_fr(t, x2);
+                st_fr(t + 1, x4);
+                st_fr(t + 2, x5);
+            }
+            s = x5;
+        }
+        sbox += full ? host::POSEIDON_T : 1;
+        const Fr p = fp_mul(ld_fr(&pc->mds[l][j]), s);
+        Fr acc = warp_get(p, 5 * j);
+#pragma unroll 1
+        for (int k = 1; k < host::POSEIDON_T; k++) acc = fp_add(acc, warp_get(p, 5 * j + k));
+        s = acc;
+    }
+}
+
+// hash_fix_len_array, warp-wide; returns the digest in every lane
+template <class GetIn>
+__device__ Fr poseidon_hash_w(int n_in, GetIn in_of, int lane, const PoseidonConsts* pc, Fr* trace) {
+    const int j = lane % 5;
+    Fr s = Fr::zero();
+    if (j == 0) s = ld_fr(&pc->two64);
+    const int chunks = n_in / host::POSEIDON_RATE + 1;
+    for (int c = 0; c < chunks; c++) {
+        const int lo = c * host::POSEIDON_RATE;
+        const int len = lo < n_in ? min(host::POSEIDON_RATE, n_in - lo) : 0;
+        if (j >= 1 && j <= len) s = fp_add(s, in_of(lo + j - 1));
+        if (len + 1 < host::POSEIDON_T && j == len + 1) s = fp_add(s, Fr::one());
+        poseidon_permute_w(s, lane, pc, trace ? trace + (size_t)c * host::POSEIDON_TRACE : nullptr);
+    }
+    return warp_get(s, 1);
+}
+
 // inputs per proof, each a Montgomery Fr, in UpdateNoteInput::new argument order:
 //   op_pub (amount, token, user) | new_note_hash | merkle_root | new_note[4] | old_note[4] |
 //   path_shape[H] | path[H] | op_priv.user | old_account (token0, balance0, token1, balance1)
-__global__ void __launch_bounds__(32) update_note_witness_kernel(const Fr* __restrict__ inputs, uint32_t n_proofs,
+// One CTA of two warps per proof, split along the data dependencies of the statement:
+//   warp 0: loaded witnesses, H(old_note), the Merkle path (the long chain: 2 + H permutations)
+//   warp 1: H(new_note), H(old_account), the balance update and its range bits, H(new_account) (6 permutations)
+__global__ void __launch_bounds__(64) update_note_witness_kernel(const Fr* __restrict__ inputs, uint32_t n_proofs,
                                                                 uint32_t H, int kind, uint32_t num_vars,
                                                                 const PoseidonConsts* __restrict__ pc,
                                                                 Fr* __restrict__ z_all, uint32_t* __restrict__ status) {
-    const int lane = threadIdx.x & 31;
-    const int l = lane & (GROUP - 1);
-    const uint32_t proof_raw = blockIdx.x * (32 / GROUP) + (lane / GROUP);
-    const bool active = proof_raw < n_proofs;
-    const uint32_t proof = active ? proof_raw : n_proofs - 1;  // idle groups shadow the last proof, no stores
+    __shared__ uint32_t ok_sh[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t proof = blockIdx.x;
+    if (proof >= n_proofs) return;
     const uint32_t n_in = 18 + 2 * H;
     const Fr* in = inputs + (size_t)proof * n_in;
     Fr* z = z_all + (size_t)proof * num_vars;
     // input slots
     const int I_AMOUNT = 0, I_TOKEN = 1, I_USER = 2, I_NNH = 3, I_ROOT = 4, I_NEW = 5, I_OLD = 9;
     const int I_SHAPE = 13, I_PATH = 13 + H, I_PRIV = 13 + 2 * H, I_ACC = 14 + 2 * H;
-    const bool wr = active && l == 0;  // the lane that writes scalar witnesses
+    // assignment layout (the allocation order of host_r1cs.hpp)
+    const uint32_t T = host::POSEIDON_TRACE;
+    const uint32_t n_copy = 4 + 3 + 2 * H + 1 + 4;
+    const uint32_t O_COPY = 7, O_NEW_HASH = O_COPY + n_copy, O_OLD_HASH = O_NEW_HASH + 2 * T, O_PATH = O_OLD_HASH + 2 * T;
+    const uint32_t O_ACC_HASH = O_PATH + H * (4 + T), O_AMOUNT_BITS = O_ACC_HASH + 2 * T;
+    const uint32_t O_UPDATE = O_AMOUNT_BITS + host::BALANCE_BITS, O_NACC_HASH = O_UPDATE + 2 * (3 + host::BALANCE_BITS);
+    const uint32_t O_END = O_NACC_HASH + 2 * T;
+    const bool wr = lane == 0;  // the lane that writes scalar witnesses
     bool ok = true;
-    uint32_t cur = 0;
-    // ---- z[0] = 1, instance variables, loaded witnesses
-    if (wr) {
-        st_fr(z + 0, Fr::one());
-        st_fr(z + 1, ld_fr(in + I_AMOUNT));
-        st_fr(z + 2, ld_fr(in + I_TOKEN));
-        st_fr(z + 3, ld_fr(in + I_USER));
-        st_fr(z + 4, ld_fr(in + I_NNH));
-        st_fr(z + 5, ld_fr(in + I_ROOT));
-        st_fr(z + 6, ld_fr(in + I_OLD + 2));  // old_note.nullifier
-    }
-    cur = 7;
-    if (active) {
+    if (warp == 0) {
+        // ---- z[0] = 1, instance variables, loaded witnesses
+        if (wr) {
+            st_fr(z + 0, Fr::one());
+            st_fr(z + 1, ld_fr(in + I_AMOUNT));
+            st_fr(z + 2, ld_fr(in + I_TOKEN));
+            st_fr(z + 3, ld_fr(in + I_USER));
+            st_fr(z + 4, ld_fr(in + I_NNH));
+            st_fr(z + 5, ld_fr(in + I_ROOT));
+            st_fr(z + 6, ld_fr(in + I_OLD + 2));  // old_note.nullifier
+        }
         // new_note[4], old zk_id, old trapdoor, old account_hash, path_shape[H], path[H], op_priv, account[4]
-        const uint32_t n_copy = 4 + 3 + 2 * H + 1 + 4;
-        for (uint32_t i = l; i < n_copy; i += GROUP) {
+        for (uint32_t i = lane; i < n_copy; i += 32) {
             uint32_t src;
             if (i < 4) src = I_NEW + i;
             else if (i < 7) src = I_OLD + (i == 4 ? 0 : i == 5 ? 1 : 3);
             else src = I_SHAPE + (i - 7);  // shape, path, op_priv, account are contiguous in the input
-            st_fr(z + cur + i, ld_fr(in + src));
+            st_fr(z + O_COPY + i, ld_fr(in + src));
         }
-    }
-    cur += 4 + 3 + 2 * H + 1 + 4;
-
-    // ---- H(new_note) == new_note_hash                               update_note.rs:129
-    Fr h_new = poseidon_hash(4, [&](int i) { return ld_fr(in + I_NEW + i); }, l, pc, active ? z + cur : nullptr);
-    cur += 2 * host::POSEIDON_TRACE;
-    ok = ok && (h_new == ld_fr(in + I_NNH));
-    // ---- old_note_hash                                               update_note.rs:131
-    Fr current = poseidon_hash(4, [&](int i) { return ld_fr(in + I_OLD + i); }, l, pc, active ? z + cur : nullptr);
-    cur += 2 * host::POSEIDON_TRACE;
-    // ---- Merkle path                                                 merkle_proof.rs:49-57
-    for (uint32_t i = 0; i < H; i++) {
-        const Fr shape = ld_fr(in + I_SHAPE + i);
-        const Fr sib = ld_fr(in + I_PATH + i);
-        const bool sel = shape.is_zero();  // selector = is_zero(shape)
-        if (wr) {
-            Fr inv = sel ? Fr::zero() : (shape == Fr::one() ? Fr::one() : fp_inv(shape));
-            st_fr(z + cur, inv);
-            st_fr(z + cur + 1, sel ? Fr::one() : Fr::zero());
+        // ---- old_note_hash                                               update_note.rs:131
+        Fr current = poseidon_hash_w(4, [&](int i) { return ld_fr(in + I_OLD + i); }, lane, pc, z + O_OLD_HASH);
+        // ---- Merkle path                                                 merkle_proof.rs:49-57
+        for (uint32_t i = 0; i < H; i++) {
+            Fr* zl = z + O_PATH + (size_t)i * (4 + T);
+            const Fr shape = ld_fr(in + I_SHAPE + i);
+            const Fr sib = ld_fr(in + I_PATH + i);
+            const bool sel = shape.is_zero();  // selector = is_zero(shape)
+            // left = select(sibling, current, selector) ; right = select(current, sibling, selector)
+            const Fr t1 = sel ? fp_sub(sib, current) : Fr::zero();
+            const Fr t2 = sel ? fp_sub(current, sib) : Fr::zero();
+            if (wr) {
+                Fr inv = sel ? Fr::zero() : (shape == Fr::one() ? Fr::one() : fp_inv(shape));
+                st_fr(zl, inv);
+                st_fr(zl + 1, sel ? Fr::one() : Fr::zero());
+                st_fr(zl + 2, t1);
+                st_fr(zl + 3, t2);
+            }
+            const Fr left = fp_add(t1, current), right = fp_add(t2, sib);
+            current = poseidon_hash_w(2, [&](int k) { return k == 0 ? left : right; }, lane, pc, zl + 4);
         }
-        cur += 2;
-        // left = select(sibling, current, selector) ; right = select(current, sibling, selector)
-        const Fr t1 = sel ? fp_sub(sib, current) : Fr::zero();
-        const Fr t2 = sel ? fp_sub(current, sib) : Fr::zero();
-        if (wr) {
-            st_fr(z + cur, t1);
-            st_fr(z + cur + 1, t2);
+        ok = ok && (current == ld_fr(in + I_ROOT));                        // merkle_proof.rs:59-60
+        ok = ok && (ld_fr(in + I_USER) == ld_fr(in + I_PRIV));             // combine(): ops.rs:47-62
+    } else {
+        // ---- H(new_note) == new_note_hash                               update_note.rs:129
+        Fr h_new = poseidon_hash_w(4, [&](int i) { return ld_fr(in + I_NEW + i); }, lane, pc, z + O_NEW_HASH);
+        ok = ok && (h_new == ld_fr(in + I_NNH));
+        // ---- H(old_account) == old_note.account_hash                     update_account.rs:79-85
+        Fr h_acc = poseidon_hash_w(4, [&](int i) { return ld_fr(in + I_ACC + i); }, lane, pc, z + O_ACC_HASH);
+        ok = ok && (h_acc == ld_fr(in + I_OLD + 3));
+        // ---- account update                                              account.rs:36-79 (mock)
+        const Fr amount = ld_fr(in + I_AMOUNT);
+        const Fr token = ld_fr(in + I_TOKEN);
+        {
+            const Fr canon = fp_from_mont(amount);
+            ok = ok && fits_bits128(canon);
+            for (int b = lane; b < host::BALANCE_BITS; b += 32)
+                st_fr(z + O_AMOUNT_BITS + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
         }
-        cur += 2;
-        const Fr left = fp_add(t1, current), right = fp_add(t2, sib);
-        current = poseidon_hash(2, [&](int k) { return k == 0 ? left : right; }, l, pc, active ? z + cur : nullptr);
-        cur += host::POSEIDON_TRACE;
-    }
-    ok = ok && (current == ld_fr(in + I_ROOT));                        // merkle_proof.rs:59-60
-    ok = ok && (ld_fr(in + I_USER) == ld_fr(in + I_PRIV));             // combine(): ops.rs:47-62
-    // ---- H(old_account) == old_note.account_hash                     update_account.rs:79-85
-    Fr h_acc = poseidon_hash(4, [&](int i) { return ld_fr(in + I_ACC + i); }, l, pc, active ? z + cur : nullptr);
-    cur += 2 * host::POSEIDON_TRACE;
-    ok = ok && (h_acc == ld_fr(in + I_OLD + 3));
-    // ---- account update                                              account.rs:36-79 (mock)
-    const Fr amount = ld_fr(in + I_AMOUNT);
-    const Fr token = ld_fr(in + I_TOKEN);
-    {
-        const Fr canon = fp_from_mont(amount);
-        ok = ok && fits_bits128(canon);
-        if (active)
-            for (int b = l; b < host::BALANCE_BITS; b += GROUP)
-                st_fr(z + cur + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
-        cur += host::BALANCE_BITS;
-    }
-    Fr new_bal[2];
-    int n_match = 0;
-    for (int i = 0; i < 2; i++) {
-        const Fr tok = ld_fr(in + I_ACC + 2 * i), bal = ld_fr(in + I_ACC + 2 * i + 1);
-        const Fr diff = fp_sub(tok, token);
-        const bool eq = diff.is_zero();
-        n_match += eq ? 1 : 0;
-        const Fr delta = eq ? amount : Fr::zero();
-        if (wr) {
-            st_fr(z + cur, eq ? Fr::zero() : fp_inv(diff));
-            st_fr(z + cur + 1, eq ? Fr::one() : Fr::zero());
-            st_fr(z + cur + 2, delta);
+        Fr new_bal[2];
+        int n_match = 0;
+        for (int i = 0; i < 2; i++) {
+            Fr* zu = z + O_UPDATE + (size_t)i * (3 + host::BALANCE_BITS);
+            const Fr tok = ld_fr(in + I_ACC + 2 * i), bal = ld_fr(in + I_ACC + 2 * i + 1);
+            const Fr diff = fp_sub(tok, token);
+            const bool eq = diff.is_zero();
+            n_match += eq ? 1 : 0;
+            const Fr delta = eq ? amount : Fr::zero();
+            if (wr) {
+                st_fr(zu, eq ? Fr::zero() : fp_inv(diff));
+                st_fr(zu + 1, eq ? Fr::one() : Fr::zero());
+                st_fr(zu + 2, delta);
+            }
+            new_bal[i] = kind == host::KIND_DEPOSIT ? fp_add(bal, delta) : fp_sub(bal, delta);
+            const Fr canon = fp_from_mont(new_bal[i]);
+            ok = ok && fits_bits128(canon);                                // checked_add / checked_sub
+            for (int b = lane; b < host::BALANCE_BITS; b += 32)
+                st_fr(zu + 3 + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
         }
-        cur += 3;
-        new_bal[i] = kind == host::KIND_DEPOSIT ? fp_add(bal, delta) : fp_sub(bal, delta);
-        const Fr canon = fp_from_mont(new_bal[i]);
-        ok = ok && fits_bits128(canon);                                // checked_add / checked_sub
-        if (active)
-            for (int b = l; b < host::BALANCE_BITS; b += GROUP)
-                st_fr(z + cur + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
-        cur += host::BALANCE_BITS;
+        ok = ok && n_match == 1;
+        // ---- H(new_account) == new_note.account_hash                     update_account.rs:88-94
+        Fr h_nacc = poseidon_hash_w(
+            4, [&](int i) { return (i & 1) ? new_bal[i >> 1] : ld_fr(in + I_ACC + i); }, lane, pc, z + O_NACC_HASH);
+        ok = ok && (h_nacc == ld_fr(in + I_NEW + 3));
     }
-    ok = ok && n_match == 1;
-    // ---- H(new_account) == new_note.account_hash                     update_account.rs:88-94
-    Fr h_nacc = poseidon_hash(
-        4, [&](int i) { return (i & 1) ? new_bal[i >> 1] : ld_fr(in + I_ACC + i); }, l, pc, active ? z + cur : nullptr);
-    cur += 2 * host::POSEIDON_TRACE;
-    ok = ok && (h_nacc == ld_fr(in + I_NEW + 3));
-    if (wr) status[proof] = (ok ? 0u : 1u) | (cur == num_vars ? 0u : 2u);
+    if (wr) ok_sh[warp] = ok ? 1u : 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) status[proof] = ((ok_sh[0] & ok_sh[1]) ? 0u : 1u) | (O_END == num_vars ? 0u : 2u);
 }
 
 // n_hashes independent hash_fix_len_array calls of the same arity (Merkle tree levels, note hashes)
@@ -258,8 +313,8 @@ int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t n
     B200ZK_TRY(poseidon_consts_device(ctx, &pc));
     {
         ProfScope ps(ctx, "witness");
-        update_note_witness_kernel<<<div_up(batch, 32 / GROUP), 32, 0, ctx->stream>>>(d_inputs, (uint32_t)batch, H, kind,
-                                                                                     num_vars, pc, d_z, d_status);
+        update_note_witness_kernel<<<(unsigned)batch, 64, 0, ctx->stream>>>(d_inputs, (uint32_t)batch, H, kind, num_vars, pc,
+                                                                            d_z, d_status);
     }
     return check_launch(ctx, "update_note_witness_kernel");
 }
