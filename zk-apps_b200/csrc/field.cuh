@@ -67,6 +67,10 @@ struct FqCfg {
                                     0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
         return m[i];
     }
+    HD static constexpr uint32_t p2(int i) {  // p^2, 24 limbs (keeps lazy Fq2 differences non-negative)
+        constexpr uint32_t m[24] = {0x1c718e39u, 0x26aa0000u, 0x76382eabu, 0x7ced6b1du, 0x62113cfdu, 0x162c3383u, 0x3e71b743u, 0x66bf91edu, 0x7091a049u, 0x292e85a8u, 0x86185c7bu, 0x1d68619cu, 0x0978ef01u, 0xf5314933u, 0x16ddca6eu, 0x50a62cfdu, 0x349e8bd0u, 0x66e59e49u, 0x0e7046b4u, 0xe2dc90e5u, 0xa22f25e9u, 0x4bd278eau, 0xb8c35fc7u, 0x02a437a4u};
+        return m[i];
+    }
     HD static constexpr uint32_t r2(int i) {  // R^2 mod p
         constexpr uint32_t m[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u,
                                     0x4c95b6d5u, 0x8de5476cu, 0x939d83c0u, 0x67eb88a9u,
@@ -273,8 +277,61 @@ HD Fp<C> fp_mul(const Fp<C>& a, const Fp<C>& b) {
     return r;
 }
 
+#if defined(__CUDA_ARCH__)
+// Montgomery reduction of a 2N-limb value T < p * 2^(32N) (word by word, same X/Y split as fp_mul):
+// T / 2^(32N) mod p, fully reduced.  The upper limbs of T enter the sliding window one per step.
 template <class C>
-HD Fp<C> fp_sqr(const Fp<C>& a) { return fp_mul(a, a); }
+DEV Fp<C> fp_redc(const uint32_t* T) {
+    constexpr int N = C::N;
+    Fp<C> r;
+    uint32_t X[N + 1], Y[N], pm[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        X[k] = T[k];
+        Y[k] = 0;
+        pm[k] = C::mod(k);
+    }
+    X[N] = 0;
+    {
+        const uint32_t m = X[0] * C::INV;
+        ptx::row_even<N>(X, pm, m);
+        ptx::row_odd<N>(Y, pm, m);
+    }
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+        uint32_t nx[N + 1], ny[N], m;
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) nx[k] = Y[k];
+#pragma unroll
+        for (int k = 0; k < N - 1; k++) ny[k] = X[k + 2];
+        ny[N - 1] = 0;
+        asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=&r"(nx[N - 1]), "=&r"(nx[N]) : "r"(Y[N - 1]), "r"(T[N - 1 + i]));
+        ptx::redc_step<N>(nx[0], m, Y[0], X[1], ny, pm, C::INV);
+#pragma unroll
+        for (int k = 0; k <= N; k++) X[k] = nx[k];
+#pragma unroll
+        for (int k = 0; k < N; k++) Y[k] = ny[k];
+        ptx::row_even<N>(X, pm, m);
+    }
+    ptx::add_n<N>(r.v, Y, X + 1);
+    r.v[N - 1] += T[2 * N - 1];
+    fp_reduce_once(r);
+    return r;
+}
+#endif
+
+// a^2: on the device the N(N+1)/2 distinct limb products are formed once (cross terms doubled), then one
+// Montgomery reduction: 78 + 156 wide multiply-adds for Fq instead of 300.
+template <class C>
+HD Fp<C> fp_sqr(const Fp<C>& a) {
+#if defined(__CUDA_ARCH__)
+    uint32_t T[2 * C::N];
+    ptx::sqr_wide<C::N>(T, a.v);
+    return fp_redc<C>(T);
+#else
+    return fp_mul(a, a);
+#endif
+}
 
 template <class C>
 HD Fp<C> fp_to_mont(const Fp<C>& a) { return fp_mul(a, Fp<C>::r2()); }
@@ -346,11 +403,35 @@ HD Fq2 fp_dbl(const Fq2& a) { return Fq2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
 // Fq2 products are out of line: a G2 accumulator does not fit the register file anyway, the
 // operands travel through L1-resident local memory (~2% of the product's issue time), and the
 // code shrinks ~10x (I-cache, ptxas time).
+// B200ZK_FQ2_LAZY (off): measured on B200 the lazy-reduction product below (744 instead of 900 wide
+// multiply-adds, bit-exact, tests green) makes the G2 bucket accumulation 7 % SLOWER (13.3 -> 14.2 ms per step):
+// the 24-limb add/sub carry chains are pure latency at 8 warps/SM and the bigger callee frame costs the caller
+// more spills.  Kept for a kernel with more resident warps.
 HD_NOINLINE Fq2 fp_mul(const Fq2& a, const Fq2& b) {  // Karatsuba, 3 Fq mul
+#if defined(__CUDA_ARCH__) && defined(B200ZK_FQ2_LAZY)
+    // lazy reduction: three unreduced 24-limb products, the Karatsuba sums on the wide values, two Montgomery
+    // reductions instead of three (3*144 + 2*156 = 744 wide multiply-adds instead of 900).
+    // c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 in [0, 2p^2);  c0 = a0 b0 - a1 b1 + p^2 in (0, 2p^2);  2p^2 < p * 2^384.
+    constexpr int N = FqCfg::N;
+    uint32_t t0[2 * N], t1[2 * N], t2[2 * N], sa[N], sb[N], pp[2 * N];
+    ptx::add_n<N>(sa, a.c0.v, a.c1.v);  // < 2p < 2^382: no reduction needed
+    ptx::add_n<N>(sb, b.c0.v, b.c1.v);
+    ptx::mul_wide<N>(t2, sa, sb);
+    ptx::mul_wide<N>(t0, a.c0.v, b.c0.v);
+    ptx::mul_wide<N>(t1, a.c1.v, b.c1.v);
+    ptx::sub_wide<N>(t2, t2, t0);
+    ptx::sub_wide<N>(t2, t2, t1);
+#pragma unroll
+    for (int k = 0; k < 2 * N; k++) pp[k] = FqCfg::p2(k);
+    ptx::add_wide<N>(t0, t0, pp);
+    ptx::sub_wide<N>(t0, t0, t1);
+    return Fq2{fp_redc<FqCfg>(t0), fp_redc<FqCfg>(t2)};
+#else
     Fq t0 = fp_mul(a.c0, b.c0);
     Fq t1 = fp_mul(a.c1, b.c1);
     Fq t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
     return Fq2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+#endif
 }
 HD_NOINLINE Fq2 fp_sqr(const Fq2& a) {  // (a0+a1)(a0-a1) + 2 a0 a1 u
     Fq t0 = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
