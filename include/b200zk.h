@@ -113,6 +113,20 @@ int b200zk_ntt_fr(b200zk_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse,
 int b200zk_ntt_fr_device(b200zk_ctx* ctx, void* d_data, uint32_t log_n, int inverse,
                          const uint8_t* coset_offset, size_t batch);
 
+/* Building blocks of the multi-GPU four-step transform (zk-apps_b200/sharded.py
+ * ShardedNTT): n = n1 * n2 over G GPUs, rank g holds local[c][j1] = x[j1 * n2 + g * C + c], C = n2 / G.
+ *   1. b200zk_ntt_fr_device(local, log n1, batch = C)           column transforms
+ *   2. b200zk_ntt_twiddle_transpose_device                       out[k][c] = in[c][k] * w_n^(+-(row0 + c) * k),
+ *      in = rows x cols Fr, out = cols x rows (chunk-major by destination rank), row0 = g * C
+ *   3. all-to-all of (n1 / G) x C chunks (NCCL), b200zk_copy2d_device to interleave them into rows
+ *   4. b200zk_ntt_fr_device(rows, log n2, batch = n1 / G)        row transforms
+ * d_in and d_out must not alias. */
+int b200zk_ntt_twiddle_transpose_device(b200zk_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n,
+                                        uint64_t rows, uint64_t cols, uint64_t row0, int inverse);
+/* strided device-to-device copy on the ctx stream (cudaMemcpy2DAsync): `height` rows of `width` bytes */
+int b200zk_copy2d_device(b200zk_ctx* ctx, void* d_dst, size_t dpitch, const void* d_src, size_t spitch,
+                         size_t width, size_t height);
+
 /* ---- K4/K5: VariableBaseMSM ------------------------------------------------------------
  * Replaces ark_ec::VariableBaseMSM::msm_bigint for G1Projective / G2Projective (ark-ec 0.4.2
  * [recall]; absent from the reference, rows a7/a8).  sum_i scalars[i] * bases[i], result affine.

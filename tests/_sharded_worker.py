@@ -32,6 +32,40 @@ class OracleBackend:
         return bytes(self.corac.msm(group, buf.numpy().copy(), ones))
 
 
+    # ---- ShardedNTT primitives on host memory (torch uint8 CPU tensors)
+    def buffer(self, nbytes):
+        return self.torch.zeros(nbytes, dtype=self.torch.uint8)
+
+    def ntt_batch(self, buf, log_len, inverse, batch):
+        out = self.corac.ntt(buf.numpy()[:batch * (32 << log_len)], log_len, inverse, None, batch)
+        buf[:len(out)] = self.torch.from_numpy(out)
+
+    def twiddle_transpose(self, src, dst, log_n, rows, cols, row0, inverse):
+        from oracle.pyref import bls12_381 as bls
+        from oracle.pyref.algos import Domain
+        w = Domain(1 << log_n).group_gen
+        if inverse:
+            w = pow(w, -1, bls.R)
+        a = src.numpy().reshape(rows, cols, 32)
+        out = np.zeros((cols, rows, 32), dtype=np.uint8)
+        for c in range(rows):
+            for k in range(cols):
+                v = bls.fr_from_mont_bytes(a[c, k].tobytes()) * pow(w, (row0 + c) * k, bls.R) % bls.R
+                out[k, c] = np.frombuffer(bls.fr_to_mont_bytes(v), dtype=np.uint8)
+        dst[:] = self.torch.from_numpy(out.reshape(-1))
+
+    def copy2d(self, dst, dst_off, dpitch, src, src_off, spitch, width, height):
+        d, s_ = dst.numpy(), src.numpy()
+        for r in range(height):
+            d[dst_off + r * dpitch:dst_off + r * dpitch + width] = s_[src_off + r * spitch:src_off + r * spitch + width]
+
+    def before_collective(self):
+        pass
+
+    def after_collective(self):
+        pass
+
+
 def run(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
@@ -54,6 +88,22 @@ def run(rank, world, port, out_dir):
             got = m.msm(util.scalars_array(ss[lo:hi]))
             want = bytes(enc([cv.mul(cv.gen, sum(a * b for a, b in zip(ks, ss)) % bls.R)]))
             assert got == want, (group, n, rank)
+        # ---- four-step NTT with one all_to_all: forward vs the single-vector oracle, then inverse round trip
+        import torch
+        for log_n in (4, 7):
+            n = 1 << log_n
+            vals = util.rand_fr(300 + log_n, n)
+            x = np.frombuffer(b"".join(bls.fr_to_mont_bytes(v) for v in vals), dtype=np.uint8).reshape(n, 32)
+            want = corac.ntt(x.reshape(-1), log_n).reshape(n, 32)
+            fwd = sharded.ShardedNTT(OracleBackend(), log_n, dist)
+            l1, l2 = fwd.log_n1, fwd.log_n2
+            local = torch.from_numpy(sharded.ntt_local_from_natural(x, l1, l2, rank, world).reshape(-1).copy())
+            out = fwd.forward(local)
+            mine = sharded.ntt_local_from_natural(want, l2, l1, rank, world).reshape(-1)      # layout L(n2, n1)
+            assert bytes(out.numpy()) == bytes(mine), ("ntt forward", log_n, rank)
+            back = fwd.swapped().inverse(out)
+            assert bytes(back.numpy()) == bytes(sharded.ntt_local_from_natural(x, l1, l2, rank, world).reshape(-1)), \
+                ("ntt round trip", log_n, rank)
         # ---- round-robin proofs: a fake prover that tags each proof with its row, so placement is checked
         batch = 7
         inputs = np.arange(batch * 4, dtype=np.uint8).reshape(batch, 4)

@@ -51,6 +51,51 @@ def test_sharded_msm_world1(ctx, group, n):
     bases.free()
 
 
+def _sharded_ntt_check(ctx, be, d, rank, world, log_n, seed):
+    """forward over `world` ranks == the single-GPU transform of the whole vector; inverse brings it back"""
+    import torch
+    n = 1 << log_n
+    x = util.rand_fr_bytes_fast(seed, n).reshape(n, 32)
+    want = z.Radix2EvaluationDomain(ctx, log_n).fft(x.reshape(-1)).reshape(n, 32)
+    fwd = sharded.ShardedNTT(be, log_n, d)
+    l1, l2 = fwd.log_n1, fwd.log_n2
+    mine = sharded.ntt_local_from_natural(x, l1, l2, rank, world).reshape(-1)
+    local = torch.from_numpy(mine.copy()).to(be.device)
+    out = fwd.forward(local)
+    ctx.sync()
+    assert bytes(out.cpu().numpy()) == bytes(sharded.ntt_local_from_natural(want, l2, l1, rank, world).reshape(-1)), log_n
+    back = fwd.swapped().inverse(out)
+    ctx.sync()
+    assert bytes(back.cpu().numpy()) == bytes(mine), log_n
+
+
+def test_twiddle_transpose(ctx):
+    """out[k][c] = in[c][k] * w_n^((row0 + c) * k), both directions, ragged tile edges"""
+    import ctypes as C
+    from oracle.pyref.algos import Domain
+    log_n, rows, cols, row0 = 7, 5, 40, 3                     # (row0 + c) * k wraps mod n
+    vals = util.rand_fr(77, rows * cols)
+    d_in = ctx.alloc(rows * cols * 32); d_out = ctx.alloc(rows * cols * 32)
+    ctx.upload(d_in, util.fr_mont_array(vals))
+    for inverse in (0, 1):
+        w = Domain(1 << log_n).group_gen
+        if inverse:
+            w = pow(w, -1, R)
+        ctx.check(z.lib().b200zk_ntt_twiddle_transpose_device(ctx.handle, C.c_void_p(d_in), C.c_void_p(d_out), log_n,
+                                                              rows, cols, row0, inverse))
+        got = util.fr_from_mont_array(ctx.download(d_out, rows * cols * 32))
+        want = [vals[c * cols + k] * pow(w, (row0 + c) * k, R) % R for k in range(cols) for c in range(rows)]
+        assert got == want
+    ctx.free(d_in); ctx.free(d_out)
+
+
+@pytest.mark.parametrize("log_n", [2, 5, 12, 17, 20])
+def test_sharded_ntt_world1(ctx, log_n):
+    import torch
+    torch.cuda.set_device(0)
+    _sharded_ntt_check(ctx, sharded.GpuBackend(ctx), None, 0, 1, log_n, 40 + log_n)
+
+
 def _nccl_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch
@@ -68,8 +113,10 @@ def _nccl_worker(rank, world, port, out_dir):
         bases = z.VariableBaseMSM.Bases(ctx, 1, pts[lo * 96:hi * 96].copy())
         m = sharded.ShardedMSM(sharded.GpuBackend(ctx), 1, bases, n, dist)
         assert m.msm(ss[lo * 32:hi * 32].copy()) == want
-        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
         bases.free()
+        for log_n in (2, 9, 16, 21):
+            _sharded_ntt_check(ctx, sharded.GpuBackend(ctx), dist, rank, world, log_n, 60 + log_n)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
         ctx.close()
     finally:
         dist.destroy_process_group()

@@ -201,6 +201,46 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams p) {
     }
 }
 
+
+// Exchange step of the multi-GPU four-step transform: out[k][c] = in[c][k] *
+// w_n^(+-(row0 + c) * k), a tiled transpose through shared memory with the inter-GPU twiddle fused into
+// it.  `in` is rows x cols (row c = one length-`cols` column transform of the global matrix, global
+// column index row0 + c), `out` is cols x rows, i.e. chunk-major by destination rank.  The twiddle
+// comes from two small tables (w^e = hi[e >> S] * lo[e & (2^S - 1)]) instead of the n/2-entry master
+// table, which at n = 2^26 would be 1 GiB per GPU.
+constexpr int TT = 32;
+__global__ void __launch_bounds__(TT * 8) ntt_twiddle_transpose_kernel(const Fr* __restrict__ in, Fr* __restrict__ out,
+                                                                      uint64_t rows, uint64_t cols, uint64_t row0,
+                                                                      const Fr* __restrict__ t_lo,
+                                                                      const Fr* __restrict__ t_hi, uint32_t S,
+                                                                      uint32_t log_n) {
+    __shared__ uint4 s_lo[TT][TT + 1], s_hi[TT][TT + 1];
+    const uint64_t c0 = (uint64_t)blockIdx.y * TT, k0 = (uint64_t)blockIdx.x * TT;
+    const uint32_t tx = threadIdx.x & (TT - 1), ty = threadIdx.x / TT;
+    for (uint32_t r = ty; r < TT; r += 8) {
+        const uint64_t c = c0 + r, k = k0 + tx;
+        if (c < rows && k < cols) {
+            Fr x = load_fr(in + c * cols + k);
+            const uint64_t e = ((row0 + c) * k) & ((1ull << log_n) - 1);
+            if (e) {
+                Fr w = fp_mul(load_fr(t_hi + (e >> S)), load_fr(t_lo + (e & ((1ull << S) - 1))));
+                x = fp_mul(x, w);
+            }
+            s_lo[r][tx] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+            s_hi[r][tx] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+        }
+    }
+    __syncthreads();
+    for (uint32_t r = ty; r < TT; r += 8) {
+        const uint64_t k = k0 + r, c = c0 + tx;
+        if (c < rows && k < cols) {
+            uint4* q = reinterpret_cast<uint4*>(out + k * rows + c);
+            q[0] = s_lo[tx][r];
+            q[1] = s_hi[tx][r];
+        }
+    }
+}
+
 // out[i] = scale * base^i
 __global__ void pow_table_kernel(Fr base, Fr scale, Fr* out, uint64_t count) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
@@ -359,6 +399,40 @@ int b200zk_ntt_fr(b200zk_ctx* ctx, uint8_t* data, uint32_t log_n, int inverse, c
     B200ZK_TRY(b200zk_ntt_fr_device(ctx, d, log_n, inverse, coset_offset, batch));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_ntt_twiddle_transpose_device(b200zk_ctx* ctx, const void* d_in, void* d_out, uint32_t log_n, uint64_t rows,
+                                        uint64_t cols, uint64_t row0, int inverse) {
+    if (!ctx || !d_in || !d_out || d_in == d_out) return B200ZK_ERR_BAD_ARG;
+    if (log_n > 32) return fail(ctx, B200ZK_ERR_DOMAIN_TOO_LARGE, "log_n > 32");
+    if (rows == 0 || cols == 0) return B200ZK_OK;
+    if (div_up(rows, TT) > 65535u) return fail(ctx, B200ZK_ERR_BAD_ARG, "too many rows for one launch");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr w = host_root_of_unity(log_n);
+    if (inverse) w = fp_inv(w);
+    const uint32_t S = (log_n + 1) / 2;
+    Fr w_hi = w;
+    for (uint32_t i = 0; i < S; i++) w_hi = fp_sqr(w_hi);
+    const Fr *t_lo, *t_hi;
+    const uint64_t key = (4ull << 56) | ((uint64_t)(inverse ? 1 : 0) << 40) | ((uint64_t)log_n << 8);
+    B200ZK_TRY(get_table(ctx, key | 0, w, Fr::one(), 1ull << S, &t_lo));
+    B200ZK_TRY(get_table(ctx, key | 1, w_hi, Fr::one(), 1ull << (log_n - S), &t_hi));
+    dim3 grid(div_up(cols, TT), div_up(rows, TT));
+    {
+        ProfScope ps(ctx, "ntt_twiddle_transpose");
+        ntt_twiddle_transpose_kernel<<<grid, TT * 8, 0, ctx->stream>>>((const Fr*)d_in, (Fr*)d_out, rows, cols, row0, t_lo,
+                                                                        t_hi, S, log_n);
+    }
+    return check_launch(ctx, "ntt_twiddle_transpose_kernel");
+}
+
+int b200zk_copy2d_device(b200zk_ctx* ctx, void* d_dst, size_t dpitch, const void* d_src, size_t spitch, size_t width,
+                         size_t height) {
+    if (!ctx || !d_dst || !d_src) return B200ZK_ERR_BAD_ARG;
+    if (width == 0 || height == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    B200ZK_CUDA(ctx, cudaMemcpy2DAsync(d_dst, dpitch, d_src, spitch, width, height, cudaMemcpyDeviceToDevice, ctx->stream));
     return B200ZK_OK;
 }
 

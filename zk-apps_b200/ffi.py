@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
             "b200zk_fixed_base_mul_device": (i32, [vp, i32, vp, sz, vp]),
             "b200zk_ntt_fr": (i32, [vp, vp, u32, i32, vp, sz]),
             "b200zk_ntt_fr_device": (i32, [vp, vp, u32, i32, vp, sz]),
+            "b200zk_ntt_twiddle_transpose_device": (i32, [vp, vp, vp, u32, C.c_uint64, C.c_uint64, C.c_uint64, i32]),
+            "b200zk_copy2d_device": (i32, [vp, vp, sz, vp, sz, sz, sz]),
             "b200zk_msm_g1": (i32, [vp, vp, vp, vp, sz, vp, vp]),
             "b200zk_msm_g2": (i32, [vp, vp, vp, vp, sz, vp, vp]),
             "b200zk_bases_upload": (i32, [vp, i32, vp, vp, sz, i32, C.POINTER(vp)]),
