@@ -45,7 +45,10 @@ typedef enum {
     B200ZK_ERR_CUDA = -4,
     B200ZK_ERR_NO_DEVICE = -5,
     B200ZK_ERR_UNSATISFIED = -6,      /* witness does not satisfy the relation (ark: SynthesisError::Unsatisfiable) */
-    B200ZK_ERR_NOT_IMPLEMENTED = -7
+    B200ZK_ERR_NOT_IMPLEMENTED = -7,
+    B200ZK_ERR_MERKLE_LIMIT_EXCEEDED = -8,    /* ShielderError::MerkleTreeLimitExceeded   (contract/merkle.rs:49-51) */
+    B200ZK_ERR_MERKLE_PROOF_GEN_FAIL = -9,    /* ShielderError::MerkleTreeProofGenFail    (contract/merkle.rs:91-93) */
+    B200ZK_ERR_MERKLE_NON_EXISTING_NODE = -10 /* ShielderError::MerkleTreeNonExistingNode (contract/merkle.rs:42-46) */
 } b200zk_status;
 
 enum { B200ZK_FIELD_FR = 0, B200ZK_FIELD_FQ = 1, B200ZK_FIELD_FQ2 = 2 };
@@ -192,6 +195,38 @@ int b200zk_poseidon_constants(uint8_t* round_constants, uint8_t* mds);
 int b200zk_poseidon_hash_batch(b200zk_ctx* ctx, const uint8_t* inputs, size_t n_hashes, uint32_t arity, uint8_t* out);
 int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
                                      uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status);
+
+/* ---- the note tree (csrc/merkle.cu) -----------------------------------
+ * Replaces the reference's MerkleTree<DEPTH> (shielder/contract/merkle.rs:11-106) with the circuit's hash:
+ * node = Poseidon hash_fix_len_array(&[left, right]) (relations/src/merkle_proof.rs:49-57) instead of SHA-256
+ * (merkle.rs:24-28).  Same indexing and the same observable behaviour: heap layout, root = node 1, leaves at
+ * size + idx, a node never written reads as 0 (an empty subtree is 0, not H(0,0)); add_leaf on a full tree ->
+ * MERKLE_LIMIT_EXCEEDED; root of an empty tree -> MERKLE_NON_EXISTING_NODE; gen_proof on a FULL tree ->
+ * MERKLE_PROOF_GEN_FAIL (merkle.rs:91-93, kept as is).  Leaves, nodes and roots are 32 B Montgomery Fr.
+ *   b200zk_merkle_add_leaves = n x add_leaf (merkle.rs:48-80) in one call: n + n/2 + ... hashes.  All or nothing:
+ *     if the n leaves do not fit none is added.  first_leaf_id (may be NULL) = id of leaves[0].  roots_out (may be
+ *     NULL): n x 32 B, the root after each single insertion, i.e. what the contract pushes into roots_log.
+ *     With log_roots != 0 at creation those n roots are also kept (host side) for is_historical_root.
+ *   b200zk_merkle_gen_proofs = gen_proof (merkle.rs:89-102) for n leaves: path_out n x depth x 32 B (sibling per
+ *     level, leaf level first), shape_out (may be NULL) n x depth bytes = MerkleProof::path_shape
+ *     (merkle_proof.rs:11-14): 1 when the node on the path is the left child at that level.
+ *   b200zk_merkle_fill_update_note_inputs_device: writes path_shape[H] (as Fr 0/1), path[H] and merkle_root into
+ *     n device-resident input rows of b200zk_update_note_prove_batch_device (row = 18 + 2H Fr, H = depth), so a
+ *     batch goes tree -> witness -> proof without touching the host.  d_leaf_ids: n x u64, each < 2^depth.
+ *     Asynchronous on the ctx stream. */
+typedef struct b200zk_merkle b200zk_merkle;
+int b200zk_merkle_new(b200zk_ctx* ctx, uint32_t depth /* 1..31 */, int log_roots, b200zk_merkle** out);
+void b200zk_merkle_free(b200zk_ctx* ctx, b200zk_merkle* t);
+int b200zk_merkle_info(const b200zk_merkle* t, uint32_t* depth, uint64_t* size, uint64_t* next_leaf_idx);
+int b200zk_merkle_add_leaves(b200zk_ctx* ctx, b200zk_merkle* t, const void* leaves, int leaves_on_device, size_t n,
+                             uint64_t* first_leaf_id, uint8_t* roots_out);
+int b200zk_merkle_root(b200zk_ctx* ctx, const b200zk_merkle* t, uint8_t out[32]);
+int b200zk_merkle_node(b200zk_ctx* ctx, const b200zk_merkle* t, uint64_t id, uint8_t out[32]);
+int b200zk_merkle_is_historical_root(b200zk_ctx* ctx, const b200zk_merkle* t, const uint8_t root[32], int* out);
+int b200zk_merkle_gen_proofs(b200zk_ctx* ctx, const b200zk_merkle* t, const uint64_t* leaf_ids, size_t n,
+                             uint8_t* path_out, uint8_t* shape_out);
+int b200zk_merkle_fill_update_note_inputs_device(b200zk_ctx* ctx, const b200zk_merkle* t, const void* d_leaf_ids,
+                                                 size_t n, void* d_inputs);
 
 /* ---- Groth16 ------------------------------------------------------------------------------
  * b200zk_pk_upload: a proving key produced elsewhere (ark_groth16::ProvingKey fields, affine FFI

@@ -31,6 +31,7 @@ template <class F>
 int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,
                 size_t n, int precompute);
 // relation.cu
+int poseidon_consts_device(b200zk_ctx* ctx, const host::PoseidonConsts** out);
 int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs, size_t batch,
                                Fr* d_z, uint32_t* d_status);
 

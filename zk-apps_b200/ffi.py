@@ -19,7 +19,8 @@ _FR_R = pow(2, 256, R_MOD)
 _FR_RINV = pow(_FR_R, -1, R_MOD)
 
 STATUS = {0: "OK", -1: "BAD_ARG", -2: "BAD_LEN", -3: "DOMAIN_TOO_LARGE", -4: "CUDA", -5: "NO_DEVICE",
-          -6: "UNSATISFIED", -7: "NOT_IMPLEMENTED"}
+          -6: "UNSATISFIED", -7: "NOT_IMPLEMENTED", -8: "MERKLE_LIMIT_EXCEEDED", -9: "MERKLE_PROOF_GEN_FAIL",
+          -10: "MERKLE_NON_EXISTING_NODE"}
 
 
 class B200zkError(RuntimeError):
@@ -93,6 +94,15 @@ def lib() -> C.CDLL:
             "b200zk_groth16_prove_batch": (i32, [vp, vp, vp, i32, sz, vp, vp, vp, vp]),
             "b200zk_update_note_prove_batch": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
             "b200zk_update_note_prove_batch_device": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
+            "b200zk_merkle_new": (i32, [vp, u32, i32, C.POINTER(vp)]),
+            "b200zk_merkle_free": (None, [vp, vp]),
+            "b200zk_merkle_info": (i32, [vp, C.POINTER(u32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+            "b200zk_merkle_add_leaves": (i32, [vp, vp, vp, i32, sz, C.POINTER(C.c_uint64), vp]),
+            "b200zk_merkle_root": (i32, [vp, vp, vp]),
+            "b200zk_merkle_node": (i32, [vp, vp, C.c_uint64, vp]),
+            "b200zk_merkle_is_historical_root": (i32, [vp, vp, vp, C.POINTER(i32)]),
+            "b200zk_merkle_gen_proofs": (i32, [vp, vp, vp, sz, vp, vp]),
+            "b200zk_merkle_fill_update_note_inputs_device": (i32, [vp, vp, vp, sz, vp]),
             "b200zk_stat_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double)]),
             "b200zk_stat_reset": (i32, [vp]),
         }
@@ -433,6 +443,87 @@ def poseidon_hash_batch(ctx: Context, inputs, arity: int) -> np.ndarray:
     out = np.zeros(n * 32, dtype=np.uint8)
     ctx.check(lib().b200zk_poseidon_hash_batch(ctx.handle, pi, n, arity, out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+class MerkleTree:
+    """The note tree, device-resident: the reference's `MerkleTree<DEPTH>` (shielder/contract/merkle.rs:11-106)
+    with the circuit's Poseidon-2 node hash (relations/src/merkle_proof.rs:49-57).  Method names, results and
+    error behaviour are the reference's: add_leaf -> leaf id (MERKLE_LIMIT_EXCEEDED when full), root
+    (MERKLE_NON_EXISTING_NODE when empty), is_historical_root, gen_proof (MERKLE_PROOF_GEN_FAIL once the tree is
+    full).  add_leaves / gen_proofs are the batched forms the GPU is for."""
+
+    def __init__(self, ctx: Context, depth: int = 10, log_roots: bool = True):
+        self.ctx, self.depth, self.size = ctx, depth, 1 << depth
+        self._h = C.c_void_p()
+        ctx.check(lib().b200zk_merkle_new(ctx.handle, depth, 1 if log_roots else 0, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def next_leaf_idx(self) -> int:
+        v = C.c_uint64()
+        lib().b200zk_merkle_info(self._h, None, None, C.byref(v))
+        return v.value
+
+    def add_leaves(self, leaves, want_roots: bool = False, device_ptr: int | None = None, n: int | None = None):
+        """leaves: n x 32 B Montgomery Fr (host) or a device pointer.  -> first leaf id [, roots n x 32 B]"""
+        if device_ptr is not None:
+            pl, on_dev = C.c_void_p(device_ptr), 1
+        else:
+            pl, kl = _buf(leaves)
+            on_dev, n = 0, kl.nbytes // 32
+        first = C.c_uint64()
+        roots = np.zeros(n * 32, dtype=np.uint8) if want_roots else None
+        self.ctx.check(lib().b200zk_merkle_add_leaves(self.ctx.handle, self._h, pl, on_dev, n, C.byref(first),
+                                                      roots.ctypes.data_as(C.c_void_p) if want_roots else None))
+        return (first.value, roots) if want_roots else first.value
+
+    def add_leaf(self, leaf_mont: bytes) -> int:
+        return self.add_leaves(bytes(leaf_mont))
+
+    def root(self) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        self.ctx.check(lib().b200zk_merkle_root(self.ctx.handle, self._h, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def node(self, node_id: int) -> bytes:
+        out = np.zeros(32, dtype=np.uint8)
+        self.ctx.check(lib().b200zk_merkle_node(self.ctx.handle, self._h, node_id, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def is_historical_root(self, root_mont: bytes) -> bool:
+        r = C.c_int()
+        pr, kr = _buf(bytes(root_mont))
+        self.ctx.check(lib().b200zk_merkle_is_historical_root(self.ctx.handle, self._h, pr, C.byref(r)))
+        return bool(r.value)
+
+    def gen_proofs(self, leaf_ids):
+        """-> (path uint8[n, depth, 32], path_shape uint8[n, depth])"""
+        ids = np.ascontiguousarray(np.asarray(leaf_ids, dtype=np.uint64))
+        n = ids.size
+        path = np.zeros((n, self.depth, 32), dtype=np.uint8)
+        shape = np.zeros((n, self.depth), dtype=np.uint8)
+        self.ctx.check(lib().b200zk_merkle_gen_proofs(self.ctx.handle, self._h, ids.ctypes.data_as(C.c_void_p), n,
+                                                      path.ctypes.data_as(C.c_void_p), shape.ctypes.data_as(C.c_void_p)))
+        return path, shape
+
+    def gen_proof(self, leaf_id: int):
+        """-> ([sibling bytes] * depth, [bool] * depth)"""
+        path, shape = self.gen_proofs([leaf_id])
+        return [path[0, i].tobytes() for i in range(self.depth)], [bool(b) for b in shape[0]]
+
+    def fill_update_note_inputs_device(self, d_leaf_ids: int, n: int, d_inputs: int):
+        self.ctx.check(lib().b200zk_merkle_fill_update_note_inputs_device(self.ctx.handle, self._h, C.c_void_p(d_leaf_ids),
+                                                                          n, C.c_void_p(d_inputs)))
+
+    def free(self):
+        if self._h:
+            lib().b200zk_merkle_free(self.ctx.handle, self._h)
+            self._h = None
+
+    __del__ = free
 
 
 class ProvingKey:
