@@ -3,6 +3,7 @@
 // oracle without a GPU.  Not part of the product; never loaded by it.
 #include <cstring>
 #include "../../zk-apps_b200/csrc/ec.cuh"
+#include "../../zk-apps_b200/csrc/pairing.cuh"
 using namespace b200zk;
 
 template <class F> static void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
@@ -64,5 +65,51 @@ int hc_msm_naive(int group, const uint8_t* bases, const uint8_t* scalars, size_t
 int hc_madd_chain(int group, const uint8_t* pts, const uint8_t* neg, size_t n, uint8_t* out) {
     if (group == 1) madd_chain<Fq>(pts, neg, n, out); else madd_chain<Fq2>(pts, neg, n, out);
     return 0;
+}
+// ---- pairing.cuh: tower arithmetic, Miller loop, final exponentiation, wire format
+// Fq12 = 576 B: c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 (each Fq2 = c0 || c1, Montgomery)
+int hc_fq12_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fq12 x, y, r;
+    memcpy(&x, a, sizeof(x));
+    if (b) memcpy(&y, b, sizeof(y)); else y = x;
+    switch (op) {
+        case 0: r = fq12_mul(x, y); break;
+        case 1: r = fq12_sqr(x); break;
+        case 2: r = fq12_inv(x); break;
+        case 3: r = fq12_frob(x); break;
+        case 4: r = fq12_conj(x); break;
+        case 5: r = final_exponentiation(x); break;
+        case 6: r = fq12_mul_by_014(x, y.c0.c0, y.c0.c1, y.c1.c1); break;  // sparse operand taken from y's slots 0, 1, 4
+        default: r = x;
+    }
+    memcpy(out, &r, sizeof(r));
+    return 0;
+}
+int hc_miller_loop(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
+    Affine<Fq> p; Affine<Fq2> q;
+    memcpy(&p, g1, sizeof(p)); memcpy(&q, g2, sizeof(q));
+    Fq12 f = miller_loop(p, q);
+    memcpy(out, &f, sizeof(f));
+    return 0;
+}
+int hc_pairing(const uint8_t* g1, const uint8_t* g2, uint8_t* out) {
+    Affine<Fq> p; Affine<Fq2> q;
+    memcpy(&p, g1, sizeof(p)); memcpy(&q, g2, sizeof(q));
+    Fq12 f = final_exponentiation(miller_loop(p, q));
+    memcpy(out, &f, sizeof(f));
+    return 0;
+}
+// returns the POINT_* status
+int hc_decompress(int group, const uint8_t* in, uint8_t* out) {
+    if (group == 1) { Affine<Fq> p = Affine<Fq>::inf(); int rc = g1_decompress(in, p); memcpy(out, &p, sizeof(p)); return rc; }
+    Affine<Fq2> p = Affine<Fq2>::inf(); int rc = g2_decompress(in, p); memcpy(out, &p, sizeof(p)); return rc;
+}
+int hc_compress(int group, const uint8_t* in, uint8_t* out) {
+    if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); g1_compress(p, out); return 0; }
+    Affine<Fq2> p; memcpy(&p, in, sizeof(p)); g2_compress(p, out); return 0;
+}
+int hc_in_subgroup(int group, const uint8_t* in) {
+    if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g1_b()) && ec_in_subgroup(p); }
+    Affine<Fq2> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g2_b()) && ec_in_subgroup(p);
 }
 }

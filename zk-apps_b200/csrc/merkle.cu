@@ -20,7 +20,7 @@
 #include <cstring>
 #include <set>
 
-#include "types.cuh"
+#include "poseidon.cuh"
 
 using namespace b200zk;
 using b200zk::host::PoseidonConsts;
@@ -36,19 +36,8 @@ struct b200zk_merkle {
 
 namespace {
 
-__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
-    Fr r;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    uint4 a = q[0], b = q[1];
-    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ void stg_fr(Fr* p, const Fr& r) {
-    uint4* q = reinterpret_cast<uint4*>(p);
-    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
-}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) { return poseidon_dev::ld_fr(p); }
+__device__ __forceinline__ void stg_fr(Fr* p, const Fr& r) { poseidon_dev::st_fr(p, r); }
 
 // One thread, one permutation (t = 5, R_F = 8, R_P = 56, x^5, dense MDS every round).
 __device__ __noinline__ void poseidon_permute_thread(Fr (&s)[5], const PoseidonConsts* __restrict__ pc) {
@@ -102,21 +91,56 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(Fr* __restrict__ node
     stg_fr(nodes + id, poseidon2_thread(l, r, pc));
 }
 
-// The small top of the tree in one launch: levels with at most `blockDim.x` dirty nodes, one CTA, a barrier per level
+// ---- latency path: one WARP per hash (the depth-optimised permutation of poseidon.cuh, ~8x shorter than the
+// one-thread form), for levels too small to fill the machine with threads and for single-leaf appends.
+__device__ __forceinline__ Fr poseidon2_warp(const Fr& left, const Fr& right, int lane, const PoseidonConsts* pc) {
+    return poseidon_dev::poseidon_hash_w(2, [&](int k) { return k == 0 ? left : right; }, lane, pc, nullptr);
+}
+
+// one level, one warp per node
+__global__ void __launch_bounds__(128) merkle_level_warp_kernel(Fr* __restrict__ nodes, uint64_t first_id, uint64_t count,
+                                                               const PoseidonConsts* __restrict__ pc) {
+    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= count) return;  // whole warps leave together
+    const int lane = threadIdx.x & 31;
+    const uint64_t id = first_id + i;
+    const Fr h = poseidon2_warp(ldg_fr(nodes + 2 * id), ldg_fr(nodes + 2 * id + 1), lane, pc);
+    if (lane == 0) stg_fr(nodes + id, h);
+}
+
+// The top of the tree in one launch: levels with at most 32 dirty nodes, one CTA of 32 warps, a barrier per level
 // (a chain of tiny launches would cost more than the hashing).
-__global__ void __launch_bounds__(128) merkle_top_kernel(Fr* __restrict__ nodes, uint64_t lo, uint64_t hi,
-                                                        const PoseidonConsts* __restrict__ pc) {
+__global__ void __launch_bounds__(1024) merkle_top_kernel(Fr* __restrict__ nodes, uint64_t lo, uint64_t hi,
+                                                         const PoseidonConsts* __restrict__ pc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     while (true) {
-        const uint64_t id = lo + threadIdx.x;
+        const uint64_t id = lo + warp;
         if (id <= hi) {
-            const Fr l = ldg_fr(nodes + 2 * id), r = ldg_fr(nodes + 2 * id + 1);
-            stg_fr(nodes + id, poseidon2_thread(l, r, pc));
+            const Fr h = poseidon2_warp(ldg_fr(nodes + 2 * id), ldg_fr(nodes + 2 * id + 1), lane, pc);
+            if (lane == 0) stg_fr(nodes + id, h);
         }
         if (lo == 1) break;
         lo >>= 1;
         hi >>= 1;
         __syncthreads();
     }
+}
+
+// historical roots, one warp per inserted leaf (small batches)
+__global__ void __launch_bounds__(128) merkle_roots_warp_kernel(const Fr* __restrict__ nodes, uint64_t size, uint64_t first,
+                                                               uint64_t n, uint32_t depth,
+                                                               const PoseidonConsts* __restrict__ pc, Fr* __restrict__ roots) {
+    const uint64_t k = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const int lane = threadIdx.x & 31;
+    uint64_t id = size + first + k;
+    Fr cur = ldg_fr(nodes + id);
+    for (uint32_t lvl = 0; lvl < depth; lvl++) {
+        if (id & 1) cur = poseidon2_warp(ldg_fr(nodes + (id ^ 1)), cur, lane, pc);
+        else cur = poseidon2_warp(cur, Fr::zero(), lane, pc);
+        id >>= 1;
+    }
+    if (lane == 0) stg_fr(roots + k, cur);
 }
 
 // root after the insertion of leaf (first + k), k < n: walk up with the finished left siblings and 0 on the right
@@ -153,18 +177,27 @@ __global__ void merkle_paths_kernel(const Fr* __restrict__ nodes, uint64_t size,
     if (shape_fr) stg_fr(shape_fr + k * shape_stride + lvl, left ? Fr::one() : Fr::zero());
 }
 
+// Up to this many hashes a launch runs one warp per hash (latency), above it one thread per hash (throughput):
+// 148 SMs x 32 resident warps of the warp-wide permutation.
+constexpr uint64_t WARP_PATH_MAX = 4096;
+
 int rebuild_levels(b200zk_ctx* ctx, b200zk_merkle* t, uint64_t first, uint64_t n, const PoseidonConsts* pc) {
     uint64_t lo = (t->size + first) >> 1, hi = (t->size + first + n - 1) >> 1;
     ProfScope ps(ctx, "merkle_levels");
     for (uint32_t lvl = 0; lvl < t->depth; lvl++) {
         const uint64_t count = hi - lo + 1;
-        if (count <= 128) {
-            merkle_top_kernel<<<1, 128, 0, ctx->stream>>>(t->d_nodes, lo, hi, pc);
+        if (count <= 32) {
+            merkle_top_kernel<<<1, 1024, 0, ctx->stream>>>(t->d_nodes, lo, hi, pc);
             B200ZK_TRY(check_launch(ctx, "merkle_top_kernel"));
             break;
         }
-        merkle_level_kernel<<<div_up(count, 128), 128, 0, ctx->stream>>>(t->d_nodes, lo, count, pc);
-        B200ZK_TRY(check_launch(ctx, "merkle_level_kernel"));
+        if (count <= WARP_PATH_MAX) {
+            merkle_level_warp_kernel<<<div_up(count, 4), 128, 0, ctx->stream>>>(t->d_nodes, lo, count, pc);
+            B200ZK_TRY(check_launch(ctx, "merkle_level_warp_kernel"));
+        } else {
+            merkle_level_kernel<<<div_up(count, 128), 128, 0, ctx->stream>>>(t->d_nodes, lo, count, pc);
+            B200ZK_TRY(check_launch(ctx, "merkle_level_kernel"));
+        }
         lo >>= 1;
         hi >>= 1;
     }
@@ -243,8 +276,12 @@ int b200zk_merkle_add_leaves(b200zk_ctx* ctx, b200zk_merkle* t, const void* leav
         B200ZK_TRY(scratch(ctx, "merkle_roots", n * sizeof(Fr), &d_roots));
         {
             ProfScope ps(ctx, "merkle_roots");
-            merkle_roots_kernel<<<div_up(n, 128), 128, 0, ctx->stream>>>(t->d_nodes, t->size, first, n, t->depth, pc,
-                                                                         (Fr*)d_roots);
+            if (n <= WARP_PATH_MAX)
+                merkle_roots_warp_kernel<<<div_up(n, 4), 128, 0, ctx->stream>>>(t->d_nodes, t->size, first, n, t->depth, pc,
+                                                                                (Fr*)d_roots);
+            else
+                merkle_roots_kernel<<<div_up(n, 128), 128, 0, ctx->stream>>>(t->d_nodes, t->size, first, n, t->depth, pc,
+                                                                             (Fr*)d_roots);
         }
         B200ZK_TRY(check_launch(ctx, "merkle_roots_kernel"));
         std::vector<uint8_t> tmp;
