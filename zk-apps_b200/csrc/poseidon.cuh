@@ -35,7 +35,7 @@ __device__ __forceinline__ Fr warp_get(const Fr& v, int src) {
     return r;
 }
 
-__device__ void poseidon_permute_w(Fr& s, int lane, const PoseidonConsts* pc, Fr* trace) {
+static __device__ void poseidon_permute_w(Fr& s, int lane, const PoseidonConsts* pc, Fr* trace) {
     const int half = host::POSEIDON_RF / 2;
     const int j = lane % 5, l = lane < 25 ? lane / 5 : 0;  // lanes 25..31 shadow row 0; nobody reads them
     int sbox = 0;
