@@ -36,6 +36,7 @@ extern "C" {
 typedef struct b200zk_ctx b200zk_ctx;
 typedef struct b200zk_bases b200zk_bases;   /* device-resident MSM bases (proving-key query) */
 typedef struct b200zk_pk b200zk_pk;         /* device-resident Groth16 proving key + R1CS matrices */
+typedef struct b200zk_vk b200zk_vk;         /* device-resident prepared verifying key */
 
 typedef enum {
     B200ZK_OK = 0,
@@ -48,7 +49,8 @@ typedef enum {
     B200ZK_ERR_NOT_IMPLEMENTED = -7,
     B200ZK_ERR_MERKLE_LIMIT_EXCEEDED = -8,    /* ShielderError::MerkleTreeLimitExceeded   (contract/merkle.rs:49-51) */
     B200ZK_ERR_MERKLE_PROOF_GEN_FAIL = -9,    /* ShielderError::MerkleTreeProofGenFail    (contract/merkle.rs:91-93) */
-    B200ZK_ERR_MERKLE_NON_EXISTING_NODE = -10 /* ShielderError::MerkleTreeNonExistingNode (contract/merkle.rs:42-46) */
+    B200ZK_ERR_MERKLE_NON_EXISTING_NODE = -10,/* ShielderError::MerkleTreeNonExistingNode (contract/merkle.rs:42-46) */
+    B200ZK_ERR_BAD_ENCODING = -11             /* serialized key: truncated / invalid point (ark SerializationError::InvalidData) */
 } b200zk_status;
 
 enum { B200ZK_FIELD_FR = 0, B200ZK_FIELD_FQ = 1, B200ZK_FIELD_FQ2 = 2 };
@@ -259,6 +261,57 @@ int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const u
 int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,
                                           const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
                                           uint8_t* out_status);
+
+/* ---- Groth16 verifier and wire formats ------------------------
+ * Replaces the mock the contract calls where a verifier would sit: ZkProof::verify_creation /
+ * verify_update (shielder/mocked_zk/src/relations.rs:127-155; call sites shielder/contract/lib.rs:56,74)
+ * with ark_groth16::Groth16::verify_proof over a PreparedVerifyingKey [recall]:
+ *     e(A, B) * e(L, -gamma) * e(C, -delta) == e(alpha, beta),  L = gamma_abc[0] + sum x_i gamma_abc[i+1].
+ * b200zk_vk_upload: vk in b200zk_groth16_setup's vk_out layout (alpha_g1 96 | beta_g2 192 | gamma_g2 192 |
+ *   delta_g2 192 | gamma_abc_g1 num_inputs*96, num_inputs counts the constant ONE); e(alpha, beta) is
+ *   evaluated once here (process_vk).
+ * b200zk_groth16_verify_batch: proofs = batch * 192 B compressed A|B|C; public_inputs = batch *
+ *   (num_inputs-1) * 32 B Montgomery Fr (ark `&[Fr]`, the ONE is implicit); both host or both device.
+ *   status_out (host, one per proof) receives a b200zk_proof_status: never an aggregate verdict.
+ *   check_subgroup != 0 also tests [r]P = O on A, B, C (ark Validate::Yes on deserialisation).
+ * b200zk_groth16_verify_aggregate: ONE verdict for the whole batch from a random linear combination
+ *   (prod e(r_i A_i, B_i) = e(alpha,beta)^(sum r_i) e(sum r_i L_i, gamma) e(sum r_i C_i, delta)): batch + 3
+ *   Miller loops and one final exponentiation instead of 3 * batch and batch.  coeffs = batch * 16 B
+ *   little-endian 128-bit randomisers chosen by the CALLER (soundness error 2^-128 over their choice).
+ *   *all_valid = 1 iff every proof decodes and the combined equation holds.
+ * b200zk_points_compress / _decompress: the zcash / ark-serialize compressed encoding (48 B G1, 96 B G2:
+ *   big-endian x, flag bits 0x80 compressed, 0x40 infinity, 0x20 y lexicographically largest; G2 = x.c1|x.c0),
+ *   one thread per point; decompress status per point: 0 ok, 1 bad encoding, 2 not on curve, 3 not in subgroup.
+ * b200zk_vk_serialize / _deserialize: ark CanonicalSerialize (compressed) of VerifyingKey [recall]:
+ *   alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | u64 LE len | gamma_abc_g1.   *len = 336 + 8 + 48*num_inputs.
+ * b200zk_pk_serialize / _deserialize: ProvingKey [recall]: vk | beta_g1 | delta_g1 | a_query | b_g1_query |
+ *   b_g2_query | h_query | l_query, every Vec as u64 LE length + compressed points.  Call _serialize with
+ *   out == NULL to get *len.  _deserialize validates encodings always and subgroup membership on request. */
+typedef enum {
+    B200ZK_PROOF_ACCEPTED = 0,
+    B200ZK_PROOF_REJECTED = 1,
+    B200ZK_PROOF_BAD_ENCODING = 2,
+    B200ZK_PROOF_NOT_ON_CURVE = 3,
+    B200ZK_PROOF_NOT_IN_SUBGROUP = 4,
+    B200ZK_PROOF_BAD_INPUT = 5
+} b200zk_proof_status;
+int b200zk_vk_upload(b200zk_ctx* ctx, const uint8_t* vk, uint32_t num_inputs, b200zk_vk** out);
+void b200zk_vk_free(b200zk_ctx* ctx, b200zk_vk* vk);
+int b200zk_vk_num_inputs(const b200zk_vk* vk, uint32_t* num_inputs);
+int b200zk_vk_export(const b200zk_vk* vk, uint8_t* out /* 672 + 96 * num_inputs */);
+int b200zk_groth16_verify_batch(b200zk_ctx* ctx, const b200zk_vk* vk, const void* proofs, const void* public_inputs,
+                                int on_device, size_t batch, int check_subgroup, int32_t* status_out);
+int b200zk_groth16_verify_aggregate(b200zk_ctx* ctx, const b200zk_vk* vk, const void* proofs, const void* public_inputs,
+                                    int on_device, size_t batch, const uint8_t* coeffs, int check_subgroup,
+                                    int* all_valid);
+int b200zk_points_compress(b200zk_ctx* ctx, int group, const uint8_t* affine, size_t n, uint8_t* out);
+int b200zk_points_decompress(b200zk_ctx* ctx, int group, const uint8_t* in, size_t n, int check_subgroup,
+                             uint8_t* out_affine, int32_t* status);
+int b200zk_vk_serialize(b200zk_ctx* ctx, const b200zk_vk* vk, uint8_t* out, size_t* len);
+int b200zk_vk_deserialize(b200zk_ctx* ctx, const uint8_t* in, size_t len, int check_subgroup, b200zk_vk** out);
+int b200zk_pk_serialize(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_vk* vk, uint8_t* out, size_t* len);
+int b200zk_pk_deserialize(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* in, size_t len, int check_subgroup,
+                          int precompute, b200zk_pk** pk_out, b200zk_vk** vk_out);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,9 @@ def groth16():
         proof = og.proof_via_scalars(M, sc, tox, cs.z, 5, 7)
         vk = og.verifying_key_from_toxic(sc, tox)
         assert og.verify_with_vk(vk, w.public_inputs(), proof)
+        # ark CanonicalSerialize (compressed) of VerifyingKey [recall]: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | u64 LE len | gamma_abc_g1
+        vk_ser = (bls.g1_compress(vk[0]) + bls.g2_compress(vk[1]) + bls.g2_compress(vk[2]) + bls.g2_compress(vk[3]) +
+                  len(vk[4]).to_bytes(8, "little") + b"".join(bls.g1_compress(p) for p in vk[4]))
         rows = rel.witness_to_inputs(w)
         nnz = [sum(len(r) for r in m) for m in M]
         out[name] = {"make_witness_seed": 1, "toxic": [11, 22, 33, 44, 55], "r": 5, "s": 7,
@@ -125,7 +128,7 @@ def groth16():
                      "instance_inputs_mont_hex": b"".join(bls.fr_to_mont_bytes(v) for v in rows).hex(),
                      "public_inputs": [hx(v, 32) for v in w.public_inputs()],
                      "assignment_sha256": hashlib.sha256(b"".join(bls.fr_to_mont_bytes(v) for v in cs.z)).hexdigest(),
-                     "proof_hex": og.proof_to_bytes(proof).hex()}
+                     "proof_hex": og.proof_to_bytes(proof).hex(), "vk_compressed_hex": vk_ser.hex()}
     return out
 
 

@@ -4,6 +4,8 @@
 #include <cstring>
 #include "../../zk-apps_b200/csrc/ec.cuh"
 #include "../../zk-apps_b200/csrc/pairing.cuh"
+#include "../../zk-apps_b200/csrc/verify.cuh"
+#include <vector>
 using namespace b200zk;
 
 template <class F> static void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
@@ -111,5 +113,17 @@ int hc_compress(int group, const uint8_t* in, uint8_t* out) {
 int hc_in_subgroup(int group, const uint8_t* in) {
     if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g1_b()) && ec_in_subgroup(p); }
     Affine<Fq2> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g2_b()) && ec_in_subgroup(p);
+}
+// the verifier's per-proof logic (verify.cuh) end to end: vk in b200zk_groth16_setup's vk_out layout; returns PROOF_*
+int hc_verify(const uint8_t* vk_raw, uint32_t num_inputs, const uint8_t* proof, const uint8_t* public_inputs, int check_subgroup) {
+    Affine<Fq> alpha; Affine<Fq2> g2s[3];
+    memcpy(&alpha, vk_raw, 96); memcpy(g2s, vk_raw + 96, 576);
+    std::vector<Affine<Fq>> abc(num_inputs);
+    memcpy(abc.data(), vk_raw + 672, (size_t)num_inputs * 96);
+    std::vector<Fr> x(num_inputs ? num_inputs - 1 : 0);
+    if (!x.empty()) memcpy(x.data(), public_inputs, x.size() * 32);
+    PreparedVk pv;
+    prepare_vk(alpha, g2s[0], g2s[1], g2s[2], pv);
+    return verify_one(pv, abc.data(), num_inputs - 1, proof, x.data(), check_subgroup != 0);
 }
 }

@@ -10,6 +10,7 @@
 //   4. assembly:  A = alpha + sum a_i z_i + r delta ;  B = beta + sum b_i z_i + s delta  (G1 and G2)
 //                 C = sum l_i aux_i + sum h_i H_i + s A + r B1 - r s delta
 //      and zcash-style compression to 48 + 96 + 48 bytes, all on the device.
+#include <algorithm>
 #include <cstring>
 #include <memory>
 
@@ -652,6 +653,119 @@ int b200zk_pk_export_query(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint
                             : which == 3 ? &pk->l_query : &pk->h_query;
     if (count) *count = h->n;
     if (out) B200ZK_CUDA(ctx, cudaMemcpy(out, h->d_points, h->n * (h->group == 1 ? 96 : 192), cudaMemcpyDeviceToHost));
+    return B200ZK_OK;
+}
+
+// ---- ark CanonicalSerialize (compressed) of ProvingKey [recall; SURVEY.md Appendix B]:
+//   vk | beta_g1 | delta_g1 | a_query | b_g1_query | b_g2_query | h_query | l_query, Vec = u64 LE length + points.
+int b200zk_pk_serialize(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_vk* vk, uint8_t* out, size_t* len) {
+    if (!ctx || !pk || !vk || !len) return B200ZK_ERR_BAD_ARG;
+    size_t vk_len = 0;
+    B200ZK_TRY(b200zk_vk_serialize(ctx, vk, nullptr, &vk_len));
+    const b200zk_bases* q[5] = {&pk->a_query, &pk->b_g1_query, &pk->b_g2_query, &pk->h_query, &pk->l_query};
+    size_t need = vk_len + 96;
+    for (auto* h : q) need += 8 + h->n * (h->group == 1 ? 48 : 96);
+    if (!out) {
+        *len = need;
+        return B200ZK_OK;
+    }
+    if (*len < need) return fail(ctx, B200ZK_ERR_BAD_LEN, "pk_serialize: buffer too small");
+    *len = need;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t off = vk_len;
+    B200ZK_TRY(b200zk_vk_serialize(ctx, vk, out, &vk_len));
+    uint8_t singles[192];
+    memcpy(singles, &pk->beta_g1, 96);
+    memcpy(singles + 96, &pk->delta_g1, 96);
+    B200ZK_TRY(b200zk_points_compress(ctx, 1, singles, 2, out + off));
+    off += 96;
+    for (auto* h : q) {
+        const uint64_t n = h->n;
+        const size_t w = h->group == 1 ? 48 : 96;
+        for (int i = 0; i < 8; i++) out[off + i] = (uint8_t)(n >> (8 * i));
+        off += 8;
+        if (n) {
+            void* d;
+            B200ZK_TRY(scratch(ctx, "wire_out", n * 2 * w, &d));
+            B200ZK_TRY(points_compress_device(ctx, h->group, h->d_points, n, (uint8_t*)d));
+            B200ZK_CUDA(ctx, cudaMemcpyAsync(out + off, d, n * w, cudaMemcpyDeviceToHost, ctx->stream));
+            B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        off += n * w;
+    }
+    return B200ZK_OK;
+}
+
+int b200zk_pk_deserialize(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* in, size_t len, int check_subgroup,
+                          int precompute, b200zk_pk** pk_out, b200zk_vk** vk_out) {
+    if (!ctx || !r || !in || !pk_out) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto rd_u64 = [&](size_t off) {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++) v |= (uint64_t)in[off + i] << (8 * i);
+        return v;
+    };
+    if (len < 344) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: truncated");
+    const uint64_t ni = rd_u64(336);
+    if (ni > (1u << 24)) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: bad gamma_abc length");
+    const size_t vk_len = 344 + (size_t)ni * 48;
+    if (len < vk_len + 96) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: truncated");
+    std::unique_ptr<b200zk_pk, void (*)(b200zk_pk*)> pk(new b200zk_pk(), free_pk);
+    B200ZK_TRY(pk_common(ctx, r, pk.get()));
+    const uint32_t nv = pk->num_inputs + pk->num_aux, n = 1u << pk->log_n;
+    if (ni != pk->num_inputs) return fail(ctx, B200ZK_ERR_BAD_LEN, "pk_deserialize: key does not match the relation (inputs)");
+    b200zk_vk* vk = nullptr;
+    B200ZK_TRY(b200zk_vk_deserialize(ctx, in, vk_len, check_subgroup, &vk));
+    std::unique_ptr<b200zk_vk, void (*)(b200zk_vk*)> vk_guard(vk, [](b200zk_vk* v) { b200zk_vk_free(nullptr, v); });
+    std::vector<uint8_t> vk_raw(672 + (size_t)ni * 96);
+    B200ZK_TRY(b200zk_vk_export(vk, vk_raw.data()));
+    memcpy(&pk->alpha_g1, vk_raw.data(), 96);
+    memcpy(&pk->beta_g2, vk_raw.data() + 96, 192);
+    memcpy(&pk->delta_g2, vk_raw.data() + 480, 192);
+    size_t off = vk_len;
+    {
+        uint8_t singles[192];
+        int32_t st[2];
+        B200ZK_TRY(b200zk_points_decompress(ctx, 1, in + off, 2, check_subgroup, singles, st));
+        if (st[0] || st[1]) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: invalid beta_g1 / delta_g1");
+        memcpy(&pk->beta_g1, singles, 96);
+        memcpy(&pk->delta_g1, singles + 96, 96);
+        off += 96;
+    }
+    b200zk_bases* q[5] = {&pk->a_query, &pk->b_g1_query, &pk->b_g2_query, &pk->h_query, &pk->l_query};
+    const size_t want[5] = {nv, nv, nv, (size_t)n - 1, pk->num_aux};
+    const char* names[5] = {"a_query", "b_g1_query", "b_g2_query", "h_query", "l_query"};
+    for (int k = 0; k < 5; k++) {
+        const int group = k == 2 ? 2 : 1;
+        const size_t w = group == 1 ? 48 : 96;
+        if (len < off + 8) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: truncated");
+        const uint64_t cnt = rd_u64(off);
+        off += 8;
+        if (cnt != want[k])
+            return fail(ctx, B200ZK_ERR_BAD_LEN, std::string("pk_deserialize: key does not match the relation (") + names[k] + ")");
+        if (len < off + cnt * w) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: truncated");
+        void *din, *dpts, *dst;
+        B200ZK_TRY(scratch(ctx, "wire_in", std::max<size_t>(cnt, 1) * 2 * w, &din));
+        B200ZK_TRY(scratch(ctx, "wire_out", std::max<size_t>(cnt, 1) * 2 * w, &dpts));
+        B200ZK_TRY(scratch(ctx, "wire_status", std::max<size_t>(cnt, 1) * sizeof(int32_t), &dst));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(din, in + off, cnt * w, cudaMemcpyHostToDevice, ctx->stream));
+        B200ZK_TRY(points_decompress_device(ctx, group, (const uint8_t*)din, cnt, check_subgroup != 0, dpts, (int32_t*)dst));
+        std::vector<int32_t> st(cnt);
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < cnt; i++)
+            if (st[i] != 0)
+                return fail(ctx, B200ZK_ERR_BAD_ENCODING, std::string("pk_deserialize: invalid point in ") + names[k] + " at " +
+                                                              std::to_string(i) + " (status " + std::to_string(st[i]) + ")");
+        q[k]->group = group;
+        if (group == 1) B200ZK_TRY(bases_build<Fq>(ctx, q[k], (const G1Affine*)dpts, true, nullptr, cnt, precompute));
+        else B200ZK_TRY(bases_build<Fq2>(ctx, q[k], (const G2Affine*)dpts, true, nullptr, cnt, precompute));
+        off += cnt * w;
+    }
+    if (off != len) return fail(ctx, B200ZK_ERR_BAD_ENCODING, "pk_deserialize: trailing bytes");
+    B200ZK_TRY(pk_singles(ctx, pk.get()));
+    *pk_out = pk.release();
+    if (vk_out) *vk_out = vk_guard.release();
     return B200ZK_OK;
 }
 

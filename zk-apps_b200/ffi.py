@@ -103,6 +103,18 @@ def lib() -> C.CDLL:
             "b200zk_merkle_is_historical_root": (i32, [vp, vp, vp, C.POINTER(i32)]),
             "b200zk_merkle_gen_proofs": (i32, [vp, vp, vp, sz, vp, vp]),
             "b200zk_merkle_fill_update_note_inputs_device": (i32, [vp, vp, vp, sz, vp]),
+            "b200zk_vk_upload": (i32, [vp, vp, u32, C.POINTER(vp)]),
+            "b200zk_vk_free": (None, [vp, vp]),
+            "b200zk_vk_num_inputs": (i32, [vp, C.POINTER(u32)]),
+            "b200zk_vk_export": (i32, [vp, vp]),
+            "b200zk_groth16_verify_batch": (i32, [vp, vp, vp, vp, i32, sz, i32, vp]),
+            "b200zk_groth16_verify_aggregate": (i32, [vp, vp, vp, vp, i32, sz, vp, i32, C.POINTER(i32)]),
+            "b200zk_points_compress": (i32, [vp, i32, vp, sz, vp]),
+            "b200zk_points_decompress": (i32, [vp, i32, vp, sz, i32, vp, vp]),
+            "b200zk_vk_serialize": (i32, [vp, vp, vp, C.POINTER(sz)]),
+            "b200zk_vk_deserialize": (i32, [vp, vp, sz, i32, C.POINTER(vp)]),
+            "b200zk_pk_serialize": (i32, [vp, vp, vp, vp, C.POINTER(sz)]),
+            "b200zk_pk_deserialize": (i32, [vp, vp, vp, sz, i32, i32, C.POINTER(vp), C.POINTER(vp)]),
             "b200zk_stat_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double)]),
             "b200zk_stat_reset": (i32, [vp]),
         }
@@ -540,6 +552,36 @@ class ProvingKey:
                                                     C.byref(cnt)))
         return out
 
+    def verifying_key(self) -> "VerifyingKey":
+        if self.vk is None:
+            raise B200zkError(-1, "this proving key was uploaded without its verifying key")
+        return VerifyingKey(self.ctx, self.vk, self.relation.num_inputs)
+
+    def serialize(self, vk: "VerifyingKey | None" = None) -> bytes:
+        """ark CanonicalSerialize (compressed) of ProvingKey."""
+        own = vk is None
+        vk = vk or self.verifying_key()
+        n = C.c_size_t()
+        self.ctx.check(lib().b200zk_pk_serialize(self.ctx.handle, self._h, vk._h, None, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        self.ctx.check(lib().b200zk_pk_serialize(self.ctx.handle, self._h, vk._h, out.ctypes.data_as(C.c_void_p),
+                                                 C.byref(n)))
+        if own:
+            vk.free()
+        return bytes(out[:n.value])
+
+    @classmethod
+    def deserialize(cls, ctx: Context, relation: "UpdateNoteRelation", data: bytes, check_subgroup: bool = False,
+                    precompute: bool = True) -> "ProvingKey":
+        pd, kd = _buf(data)
+        h, hv = C.c_void_p(), C.c_void_p()
+        ctx.check(lib().b200zk_pk_deserialize(ctx.handle, relation.handle, pd, len(data), 1 if check_subgroup else 0,
+                                              1 if precompute else 0, C.byref(h), C.byref(hv)))
+        vk = VerifyingKey(ctx, handle=hv)
+        raw = vk.export()
+        vk.free()
+        return cls(ctx, relation, h, raw)
+
     def free(self):
         if self._h:
             lib().b200zk_pk_free(self.ctx.handle, self._h)
@@ -548,8 +590,114 @@ class ProvingKey:
     __del__ = free
 
 
+PROOF_STATUS = {0: "accepted", 1: "rejected", 2: "bad encoding", 3: "not on curve", 4: "not in subgroup", 5: "bad input"}
+
+
+def points_compress(ctx: Context, group: int, affine) -> np.ndarray:
+    """Affine FFI points -> zcash / ark-serialize compressed bytes (48 B G1, 96 B G2)."""
+    pa, ka = _buf(affine)
+    n = ka.size // (96 if group == 1 else 192)
+    out = np.zeros(n * (48 if group == 1 else 96), dtype=np.uint8)
+    ctx.check(lib().b200zk_points_compress(ctx.handle, group, pa, n, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def points_decompress(ctx: Context, group: int, data, check_subgroup: bool = True):
+    """-> (affine FFI points, int32 status per point: 0 ok, 1 bad encoding, 2 not on curve, 3 not in subgroup)."""
+    pd, kd = _buf(data)
+    n = kd.size // (48 if group == 1 else 96)
+    out = np.zeros(n * (96 if group == 1 else 192), dtype=np.uint8)
+    st = np.zeros(n, dtype=np.int32)
+    ctx.check(lib().b200zk_points_decompress(ctx.handle, group, pd, n, 1 if check_subgroup else 0,
+                                             out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
+    return out, st
+
+
+class VerifyingKey:
+    """Device-resident ark_groth16::PreparedVerifyingKey (e(alpha, beta) evaluated once at upload)."""
+
+    def __init__(self, ctx: Context, vk_bytes=None, num_inputs: int | None = None, handle=None):
+        self.ctx = ctx
+        if handle is not None:
+            self._h = handle
+        else:
+            pv, kv = _buf(vk_bytes)
+            if num_inputs is None:
+                num_inputs = (kv.size - 672) // 96
+            self._h = C.c_void_p()
+            ctx.check(lib().b200zk_vk_upload(ctx.handle, pv, num_inputs, C.byref(self._h)))
+        n = C.c_uint32()
+        ctx.check(lib().b200zk_vk_num_inputs(self._h, C.byref(n)))
+        self.num_inputs = n.value
+
+    def export(self) -> np.ndarray:
+        out = np.zeros(672 + 96 * self.num_inputs, dtype=np.uint8)
+        self.ctx.check(lib().b200zk_vk_export(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def serialize(self) -> bytes:
+        """ark CanonicalSerialize (compressed) of VerifyingKey."""
+        n = C.c_size_t()
+        self.ctx.check(lib().b200zk_vk_serialize(self.ctx.handle, self._h, None, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint8)
+        self.ctx.check(lib().b200zk_vk_serialize(self.ctx.handle, self._h, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return bytes(out[:n.value])
+
+    @classmethod
+    def deserialize(cls, ctx: Context, data: bytes, check_subgroup: bool = True) -> "VerifyingKey":
+        pd, kd = _buf(data)
+        h = C.c_void_p()
+        ctx.check(lib().b200zk_vk_deserialize(ctx.handle, pd, len(data), 1 if check_subgroup else 0, C.byref(h)))
+        return cls(ctx, handle=h)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().b200zk_vk_free(self.ctx.handle, self._h)
+            self._h = None
+
+    __del__ = free
+
+
 class Groth16:
     """ark_groth16::Groth16::<Bls12_381> call sites (names per arkworks 0.4 [recall])."""
+
+    @staticmethod
+    def verify_proofs(vk: VerifyingKey, proofs, public_inputs, batch: int | None = None, check_subgroup: bool = True,
+                      device: bool = False) -> np.ndarray:
+        """Groth16::verify_proof for a batch: proofs = batch x 192 B compressed, public_inputs = batch x
+        (num_inputs - 1) Montgomery Fr (host buffers, or device pointers with device=True and batch given).
+        -> int32 status per proof (PROOF_STATUS; 0 = accepted)."""
+        ctx = vk.ctx
+        if device:
+            pp, pi = C.c_void_p(proofs), C.c_void_p(public_inputs)
+        else:
+            pp, kp = _buf(proofs)
+            pi, ki = _buf(public_inputs)
+            if batch is None:
+                batch = kp.size // 192
+        st = np.zeros(batch, dtype=np.int32)
+        ctx.check(lib().b200zk_groth16_verify_batch(ctx.handle, vk._h, pp, pi, 1 if device else 0, batch,
+                                                    1 if check_subgroup else 0, st.ctypes.data_as(C.c_void_p)))
+        return st
+
+    @staticmethod
+    def verify_proofs_aggregate(vk: VerifyingKey, proofs, public_inputs, coeffs, batch: int | None = None,
+                                check_subgroup: bool = True, device: bool = False) -> bool:
+        """One verdict for the whole batch by a random linear combination; coeffs = batch x 16 B randomisers
+        chosen by the caller."""
+        ctx = vk.ctx
+        if device:
+            pp, pi = C.c_void_p(proofs), C.c_void_p(public_inputs)
+        else:
+            pp, kp = _buf(proofs)
+            pi, ki = _buf(public_inputs)
+            if batch is None:
+                batch = kp.size // 192
+        pc, kc = _buf(coeffs)
+        ok = C.c_int()
+        ctx.check(lib().b200zk_groth16_verify_aggregate(ctx.handle, vk._h, pp, pi, 1 if device else 0, batch, pc,
+                                                        1 if check_subgroup else 0, C.byref(ok)))
+        return bool(ok.value)
 
     @staticmethod
     def generate_parameters_with_toxic_waste(ctx: Context, relation: UpdateNoteRelation, toxic, precompute=True):
