@@ -632,7 +632,10 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         static const int occ_env = getenv("B200ZK_ACC_BLOCKS") ? atoi(getenv("B200ZK_ACC_BLOCKS")) : 0;
         const int occ = occ_env ? occ_env : 2;  // measured: 3 gains 1.6 % alone but crowds out the concurrent tails
         auto kern = occ >= 4 ? msm_accumulate<F, 4> : occ == 3 ? msm_accumulate<F, 3> : msm_accumulate<F, 2>;
-        kern<<<div_up(max_runs, 128), 128, 0, st>>>(
+        // CTA width (<= 128): narrower CTAs leave registers for latency-bound CTAs of other MSMs (experiments)
+        static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
+        const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;
+        kern<<<div_up(max_runs, acc_threads), acc_threads, 0, st>>>(
             (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
             (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
@@ -649,10 +652,18 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     }
     // bucket reduction
     const uint32_t sets = (uint32_t)batch * pl.weff;
-    const uint32_t seg = std::min(pl.nb, RED_SEG), segs = pl.nb / seg;
+    // CTA shape: 256 threads x 8 buckets.  Narrower CTAs (64 or 32 threads over 512/256-bucket segments) fit in the
+    // registers two resident msm_accumulate CTAs leave free, but measured slower for the proof batch (51.2 vs
+    // 50.3 ms per step, profiles/r01_red_sweep.log): B200ZK_RED_THREADS keeps the experiment reproducible.
+    static const int red_env = getenv("B200ZK_RED_THREADS") ? atoi(getenv("B200ZK_RED_THREADS")) : 0;
+    uint32_t red_threads = RED_THREADS;
+    if (red_env == 32 || red_env == 64 || red_env == 128 || red_env == 256) red_threads = (uint32_t)red_env;
+    const uint32_t seg = std::min(pl.nb, red_threads * 8), segs = pl.nb / seg;
     uint32_t log_seg = 0;
     while ((1u << log_seg) < seg) log_seg++;
     if (segs > RED_THREADS) return fail(ctx, B200ZK_ERR_BAD_ARG, "window too large for the bucket reduction");
+    uint32_t comb_threads = 32;
+    while (comb_threads < segs) comb_threads <<= 1;
     const size_t red_smem = (size_t)RED_THREADS * sizeof(XYZZ<F>);
     B200ZK_TRY(scratch(ctx, "msm_red_a", (size_t)sets * segs * 2 * sizeof(XYZZ<F>), &d_red_a, slot));
     B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)sets + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
@@ -666,11 +677,13 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         }
         XYZZ<F>* Wseg = (XYZZ<F>*)d_red_a;
         XYZZ<F>* Rseg = Wseg + (size_t)sets * segs;
-        msm_seg_reduce<F><<<sets * segs, RED_THREADS, red_smem, st>>>((const XYZZ<F>*)d_buckets, seg, Wseg, Rseg);
+        msm_seg_reduce<F><<<sets * segs, red_threads, (size_t)red_threads * sizeof(XYZZ<F>), st>>>(
+            (const XYZZ<F>*)d_buckets, seg, Wseg, Rseg);
         B200ZK_TRY(check_launch(ctx, "msm_seg_reduce"));
         XYZZ<F>* src = Wseg;
         if (segs > 1) {
-            msm_seg_combine<F><<<sets, RED_THREADS, red_smem, st>>>(Wseg, Rseg, segs, log_seg, (XYZZ<F>*)d_red_b);
+            msm_seg_combine<F><<<sets, comb_threads, (size_t)comb_threads * sizeof(XYZZ<F>), st>>>(
+                Wseg, Rseg, segs, log_seg, (XYZZ<F>*)d_red_b);
             B200ZK_TRY(check_launch(ctx, "msm_seg_combine"));
             src = (XYZZ<F>*)d_red_b;
         }

@@ -7,7 +7,8 @@
 // Decomposition (P passes, n = n_0 * n_1 * ... * n_{P-1}, each n_p <= 2^11):
 //   pass p views the data as [outer][n_p][inner] and runs, per CTA, G adjacent `inner` columns
 //   of the length-n_p transform entirely in shared memory (DIF radix-2 stages, inner twiddles
-//   staged in shared memory once per CTA), multiplies the result by the inter-pass twiddle
+//   staged in shared memory once per CTA; three stages at a time on 8 elements held in registers,
+//   swizzled shared-memory slots), multiplies the result by the inter-pass twiddle
 //   w_M^(inner_idx * k), M = n_p * inner (fused into the store), and writes it back in place.
 //   The last pass has inner = 1 (rows are contiguous, fully coalesced loads) and scatters its
 //   outputs to the digit-reversed natural position, G consecutive rows per CTA so that the
@@ -30,7 +31,7 @@ namespace {
 
 constexpr int MAX_LOG_LEN = 11;       // longest in-CTA transform
 constexpr int LOG_TILE = 11;          // elements per CTA tile (len * G)
-constexpr int NTT_THREADS = 512;
+constexpr int NTT_THREADS = 256;      // 8 elements per thread per fused stage group
 constexpr int MAX_PASSES = 4;
 
 struct PassParams {
@@ -61,17 +62,65 @@ __device__ __forceinline__ void store_fr(Fr* p, const Fr& r) {
     q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 // shared memory keeps the two 16-byte halves of an element in separate arrays: a warp touching
-// consecutive elements then issues conflict-free LDS.128/STS.128
+// consecutive elements then issues conflict-free LDS.128/STS.128.  The slot index is swizzled by
+// XOR-folding its 3-bit groups into the low 3 bits, so that 8 lanes whose indices differ by ANY
+// power-of-two stride (radix-8 groups, bit-reversed reads, strided twiddle reads) still land in 8
+// different 16-byte bank groups; swz is a bijection of every aligned block of 8 slots.
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 __device__ __forceinline__ Fr sload(const uint4* lo, const uint4* hi, uint32_t i) {
     Fr r;
+    i = swz(i);
     uint4 a = lo[i], b = hi[i];
     r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
     r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
     return r;
 }
 __device__ __forceinline__ void sstore(uint4* lo, uint4* hi, uint32_t i, const Fr& r) {
+    i = swz(i);
     lo[i] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
     hi[i] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
+// R fused DIF radix-2 stages (s .. s+R-1) of the in-CTA transform, 2^R elements per thread in registers:
+// one shared-memory round trip and one barrier per R stages instead of per stage, and 2^R - 1 twiddle
+// loads per R * 2^(R-1) butterflies.  Element k of a group sits at index (hi * 2^R + k) * q + lo with
+// q = len >> (s + R); stage s+t pairs k with k + 2^(R-1-t); the twiddle of the pair is
+// w_len^(j << (s+t)) with j = (k mod 2^(R-1-t)) * q + lo, the position inside the half block.
+template <int R>
+__device__ __forceinline__ void stage_group(uint4* d_lo, uint4* d_hi, const uint4* t_lo, const uint4* t_hi,
+                                            uint32_t tid, uint32_t T, uint32_t tile, uint32_t log_g,
+                                            uint32_t log_len, uint32_t s) {
+    constexpr uint32_t K = 1u << R;
+    const uint32_t G = 1u << log_g;
+    const uint32_t log_q = log_len - s - R, q = 1u << log_q;
+    for (uint32_t item = tid; item < (tile >> R); item += T) {
+        const uint32_t g = item & (G - 1), grp = item >> log_g;
+        const uint32_t lo = grp & (q - 1), hi = grp >> log_q;
+        const uint32_t i0 = (hi << (log_q + R)) + lo;
+        Fr x[K];
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++) x[k] = sload(d_lo, d_hi, ((i0 + (k << log_q)) << log_g) + g);
+#pragma unroll
+        for (uint32_t t = 0; t < (uint32_t)R; t++) {
+            const uint32_t span = K >> (t + 1);
+#pragma unroll
+            for (uint32_t jj = 0; jj < span; jj++) {
+                const uint32_t j = (jj << log_q) + lo;
+                Fr w;
+                if (j != 0) w = sload(t_lo, t_hi, j << (s + t));
+#pragma unroll
+                for (uint32_t k = jj; k < K; k += 2 * span) {
+                    const Fr u = x[k], v = x[k + span];
+                    x[k] = fp_add(u, v);
+                    Fr d = fp_sub(u, v);
+                    if (j != 0) d = fp_mul(d, w);
+                    x[k + span] = d;
+                }
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++) sstore(d_lo, d_hi, ((i0 + (k << log_q)) << log_g) + g, x[k]);
+    }
 }
 
 // w_n^E for E in [0, n), from the half table; `inverse` mirrors the exponent
@@ -83,7 +132,7 @@ __device__ __forceinline__ Fr twiddle(const Fr* tw, uint32_t log_n, uint64_t E, 
     return fp_neg(load_fr(tw + (E - half)));
 }
 
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams p) {
+__global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint4 smem[];
     const uint32_t len = 1u << p.log_len, G = 1u << p.log_g, tile = len * G;
     uint4* d_lo = smem;
@@ -139,24 +188,20 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(PassParams p) {
     }
     __syncthreads();
 
-    // ---- DIF radix-2 stages
-    const uint32_t nb = tile >> 1;  // butterflies per stage
-    for (uint32_t s = 0; s < p.log_len; s++) {
-        const uint32_t log_half = p.log_len - 1 - s;
-        const uint32_t half = 1u << log_half;
-        for (uint32_t idx = tid; idx < nb; idx += T) {
-            const uint32_t g = idx & (G - 1), b = idx >> p.log_g;
-            const uint32_t j = b & (half - 1);
-            const uint32_t i0 = ((b >> log_half) << (log_half + 1)) + j;
-            const uint32_t e0 = i0 * G + g, e1 = (i0 + half) * G + g;
-            Fr u = sload(d_lo, d_hi, e0), v = sload(d_lo, d_hi, e1);
-            Fr a = fp_add(u, v);
-            Fr d = fp_sub(u, v);
-            if (half > 1 && j != 0) d = fp_mul(d, sload(t_lo, t_hi, j << s));
-            sstore(d_lo, d_hi, e0, a);
-            sstore(d_lo, d_hi, e1, d);
+    // ---- DIF radix-2 stages, three at a time in registers
+    {
+        uint32_t s = 0;
+        for (; s + 3 <= p.log_len; s += 3) {
+            stage_group<3>(d_lo, d_hi, t_lo, t_hi, tid, T, tile, p.log_g, p.log_len, s);
+            __syncthreads();
         }
-        __syncthreads();
+        if (p.log_len - s == 2) {
+            stage_group<2>(d_lo, d_hi, t_lo, t_hi, tid, T, tile, p.log_g, p.log_len, s);
+            __syncthreads();
+        } else if (p.log_len - s == 1) {
+            stage_group<1>(d_lo, d_hi, t_lo, t_hi, tid, T, tile, p.log_g, p.log_len, s);
+            __syncthreads();
+        }
     }
 
     // ---- store: position q holds output k = bitrev(q)
