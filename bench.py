@@ -335,7 +335,7 @@ def run_b200(args):
     achieved_gbs = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
     fq_mul_s = madds_per_launch * FQ_MUL_PER_MADD / (per_launch_ms * 1e-3) if per_launch_ms else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_msm_accumulate_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01_msm_accumulate_traffic_v10.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     roofline = {"kernel": "msm_accumulate<Fq> (G1 bucket accumulation, XYZZ += affine)", "bound": "hbm",

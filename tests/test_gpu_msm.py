@@ -65,7 +65,7 @@ def _gpu_bases(ctx, group, seed, n):
     return util.le_ints(ks), pts
 
 
-@pytest.mark.parametrize("group,log_n,precompute", [(1, 10, False), (1, 13, True), (1, 16, False), (1, 18, False),
+@pytest.mark.parametrize("group,log_n,precompute", [(1, 10, False), (1, 13, True), (1, 16, False), (1, 18, False), (1, 22, False),
                                                     (2, 10, False), (2, 13, True), (2, 15, False)])
 def test_sum_identity(ctx, group, log_n, precompute):
     """Exact full-size check: MSM(s, k*G) == (sum s_i k_i mod r) * G  (SURVEY.md section 8d)."""
@@ -116,3 +116,27 @@ def test_batched_shared_bases(ctx, group, precompute):
     for b in range(batch):
         assert got[b] == cv.mul(cv.gen, sum(k * s for k, s in zip(ks, ss[b * n:(b + 1) * n])) % R)
     h.free()
+
+
+@pytest.mark.parametrize("group,log_n,parts", [(1, 11, 2), (1, 12, 3), (1, 12, 4), (2, 10, 4), (1, 20, 2)])
+def test_window_group_parts(ctx, group, log_n, parts):
+    """A single plain-bases MSM cut into window groups on several streams (b200zk_set_option "msm_parts";
+    0 = the automatic choice, which splits from 2^23 points): same bytes as the unsplit pipeline, and the
+    exact sum identity."""
+    cv, enc, dec, pt = CURVES[group]
+    n = 1 << log_n
+    ks, pts = _gpu_bases(ctx, group, 300 + log_n, n)
+    sbuf = util.rand_fr_bytes_fast(400 + log_n, n)
+    want = cv.mul(cv.gen, sum(a * b for a, b in zip(ks, util.le_ints(sbuf))) % R)
+    h = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=False)
+    try:
+        ctx.set_option("msm_parts", 1)
+        one, _ = h.msm(sbuf)
+        ctx.set_option("msm_parts", parts)
+        out, inf = h.msm(sbuf)
+        out_again, _ = h.msm(sbuf)                     # scratch buffers of the part slots are reused
+    finally:
+        ctx.set_option("msm_parts", 0)
+        h.free()
+    assert not inf and dec(out)[0] == want
+    assert bytes(out) == bytes(one) == bytes(out_again)

@@ -67,6 +67,11 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
         ctx->concurrency = value != 0;
         return B200ZK_OK;
     }
+    if (strcmp(name, "msm_parts") == 0) {  // 0 = automatic, 1..4 = window groups of a single plain-bases MSM
+        if (value < 0 || value > 4) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_parts must be 0..4");
+        ctx->msm_parts = value;
+        return B200ZK_OK;
+    }
     return fail(ctx, B200ZK_ERR_BAD_ARG, std::string("unknown option ") + name);
 }
 

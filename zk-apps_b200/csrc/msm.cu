@@ -33,8 +33,9 @@ namespace {
 
 struct Plan {
     uint32_t c, windows, nb;      // nb = buckets per window = 2^(c-1)
-    uint32_t weff;                // bucket sets per msm: windows, or 1 when precomputed
+    uint32_t weff;                // bucket sets per msm: windows (of this part), or 1 when precomputed
     bool precomp;
+    uint32_t w0, w1;              // windows [w0, w1) this pass of the pipeline handles (all of them unless split)
 };
 
 // Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
@@ -66,6 +67,8 @@ Plan make_plan(size_t n, bool precomp, uint32_t c_fixed) {
     p.nb = 1u << (p.c - 1);
     p.precomp = precomp;
     p.weff = precomp ? 1 : p.windows;
+    p.w0 = 0;
+    p.w1 = p.windows;
     return p;
 }
 
@@ -111,9 +114,9 @@ __global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size
     uint32_t carry = 0;
     for (uint32_t w = 0; w < pl.windows; w++) {
         int32_t d = next_digit(k, w, pl.c, carry);
-        if (d == 0) continue;
+        if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
         uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
-        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w)) * pl.nb + bucket;
+        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
         atomicAdd(&counts[key], 1u);
     }
 }
@@ -129,9 +132,9 @@ __global__ void msm_scatter(const uint32_t* scalars, size_t n, size_t stride, si
     uint32_t carry = 0;
     for (uint32_t w = 0; w < pl.windows; w++) {
         int32_t d = next_digit(k, w, pl.c, carry);
-        if (d == 0) continue;
+        if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
         uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
-        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w)) * pl.nb + bucket;
+        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
         uint32_t pos = atomicAdd(&cursor[key], 1u);
         uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * n + i : i);
         sorted[pos] = pidx | (d < 0 ? 0x80000000u : 0u);
@@ -557,22 +560,16 @@ int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, int slot, const uint32_t* d
 
 namespace b200zk {
 
-// Device-resident batched MSM.  d_scalars: batch rows (row stride `stride` Fr elements) of n
-// scalars, canonical or Montgomery (`mont`).  d_out: batch affine points.
+// One pass of the pipeline (sort -> accumulate -> fold -> bucket reduction) over the windows [pl.w0, pl.w1) on the
+// stream of `slot`, with that slot's scratch buffers.  *sums_out: device array [batch][pl.weff] of window sums.
 template <class F>
-int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride,
-               size_t batch, bool mont, Affine<F>* d_out, int slot) {
-    if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
-    if (batch == 0) return B200ZK_OK;
+int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride, size_t batch,
+             bool mont, const Plan& pl, int slot, const XYZZ<F>** sums_out) {
     const cudaStream_t st = slot_stream(ctx, slot);
     if (!ctx->concurrency) slot = 0;
-    if (n == 0) {
-        B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), st));
-        return B200ZK_OK;
-    }
-    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0);
+    const uint32_t part_windows = pl.w1 - pl.w0;
     const uint64_t n_keys64 = (uint64_t)batch * pl.weff * pl.nb;
-    const uint64_t max_entries = (uint64_t)batch * n * pl.windows;
+    const uint64_t max_entries = (uint64_t)batch * n * part_windows;
     if (n_keys64 >= (1ull << 31) || max_entries >= (1ull << 32) || (uint64_t)h->n * pl.windows >= (1ull << 31))
         return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit bucket keys; split the batch");
     const uint32_t n_keys = (uint32_t)n_keys64;
@@ -687,7 +684,68 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
             B200ZK_TRY(check_launch(ctx, "msm_seg_combine"));
             src = (XYZZ<F>*)d_red_b;
         }
-        msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(src, (uint32_t)batch, pl.weff, pl.c, d_out);
+        *sums_out = src;
+    }
+    return B200ZK_OK;
+}
+
+// Device-resident batched MSM.  d_scalars: batch rows (row stride `stride` Fr elements) of n
+// scalars, canonical or Montgomery (`mont`).  d_out: batch affine points.
+//
+// A single MSM over plain (not precomputed) bases can be cut into up to 4 groups of windows, each a full pass
+// of the pipeline on its own stream (the caller's first, then auxiliary streams of decreasing priority), the
+// window sums meeting in one array for the Horner step.  The idea: the sort of part k+1 (atomics/HBM bound) and
+// the fold and bucket reduction of part k (latency bound) run under the bucket accumulation (multiply-pipe
+// bound) of another part.  Measured, the overlap is small -- the bucket reduction's 256-thread CTAs take whole
+// SMs away from the accumulation -- so it is on by default only from 2^23 points (2^24: 119.7 -> 117.5 ms).
+template <class F>
+int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride,
+               size_t batch, bool mont, Affine<F>* d_out, int slot) {
+    if (n > h->n) return fail(ctx, B200ZK_ERR_BAD_LEN, "more scalars than bases");
+    if (batch == 0) return B200ZK_OK;
+    const cudaStream_t st = slot_stream(ctx, slot);
+    if (n == 0) {
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), st));
+        return B200ZK_OK;
+    }
+    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0);
+    uint32_t parts = 1;
+    if (!pl.precomp && batch == 1 && slot == 0 && ctx->concurrency) {
+        if (ctx->msm_parts) parts = (uint32_t)ctx->msm_parts;
+        else if (n >= (1u << 23)) parts = 4;   // measured (profiles/r01_msm_parts_sweep.log): +2 % at 2^24, a loss below 2^22
+    }
+    parts = std::min(parts, pl.windows);
+    const XYZZ<F>* sums = nullptr;
+    if (parts == 1) {
+        B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pl, slot, &sums));
+    } else {
+        static const int part_slot[4] = {0, 5, 6, 8};   // streams: main, aux[0], aux[1], aux[3] (priority order)
+        void* d_ws;
+        B200ZK_TRY(scratch(ctx, "msm_wsums", (size_t)pl.windows * sizeof(XYZZ<F>), &d_ws, 0));
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < parts; i++) {
+            Plan pp = pl;
+            pp.w0 = w;
+            pp.w1 = w + (pl.windows - w) / (parts - i);
+            pp.weff = pp.w1 - pp.w0;
+            w = pp.w1;
+            const cudaStream_t ps = slot_stream(ctx, part_slot[i]);
+            if (i) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev_fork, 0));
+            const XYZZ<F>* part_sums = nullptr;
+            B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pp, part_slot[i], &part_sums));
+            B200ZK_CUDA(ctx, cudaMemcpyAsync((XYZZ<F>*)d_ws + pp.w0, part_sums, (size_t)pp.weff * sizeof(XYZZ<F>),
+                                             cudaMemcpyDeviceToDevice, ps));
+            if (i) {
+                B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ps));
+                B200ZK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+            }
+        }
+        sums = (const XYZZ<F>*)d_ws;
+    }
+    {
+        ProfScope ps(ctx, "msm_reduce", st);
+        msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(sums, (uint32_t)batch, pl.weff, pl.c, d_out);
         B200ZK_TRY(check_launch(ctx, "msm_finish"));
     }
     return B200ZK_OK;
