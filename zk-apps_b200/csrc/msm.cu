@@ -287,13 +287,25 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
     uint32_t v = sorted[k];
     Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
     bool neg = (v >> 31) != 0;
+    // G1: the next point is loaded into registers while the current addition runs.  G2: accumulator (96
+    // registers) + current point (48) + a second point (48) do not fit in 255 registers next to the formula's
+    // temporaries (ncu: 1.4 GB of local-memory spill traffic per launch), so the next point is only prefetched
+    // into L1 and loaded after the addition.
+    constexpr bool PREFETCH_TO_REGS = sizeof(F) == sizeof(Fq);
     for (;;) {
         const uint32_t kn = k + 1;
         Affine<F> nxt;
         uint32_t vn = 0;
         if (kn < end) {
             vn = sorted[kn];
-            nxt = load_affine(bases + (vn & 0x7fffffffu));  // in flight during the add
+            const Affine<F>* np = bases + (vn & 0x7fffffffu);
+            if constexpr (PREFETCH_TO_REGS) {
+                nxt = load_affine(np);  // in flight during the add
+            } else {
+#pragma unroll
+                for (int off = 0; off < (int)sizeof(Affine<F>); off += 128)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(np) + off));
+            }
         }
         ec_madd(acc, cur, neg);
         if (kn >= end) break;
@@ -305,7 +317,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
                 bend = offsets[key + 1];
             } while (bend == kn);
         }
-        cur = nxt;
+        if constexpr (PREFETCH_TO_REGS) cur = nxt;
+        else cur = load_affine(bases + (vn & 0x7fffffffu));
         neg = (vn >> 31) != 0;
         k = kn;
     }
