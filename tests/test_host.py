@@ -183,3 +183,24 @@ def test_host_scalar_mul_and_sum(hc, group):
         out = np.zeros(96 * group, dtype=np.uint8)
         hc.hc_msm_naive(group, _p(enc(bases)), _p(util.scalars_array(scalars)), 4, _p(out))
         assert dec(out)[0] == cv.mul(cv.gen, want)
+
+
+def test_rust_sys_bindings_match_header():
+    """rust/b200zk-sys/src/lib.rs is generated from include/b200zk.h (tools/gen_rust_sys.py): it must not be
+    stale, and every `sys::` item the arkworks-shaped shim uses must exist in it.  (Source only: no Rust
+    toolchain in this image -- SURVEY.md section 8f rank 4.)"""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_sys.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    sys_rs = open(os.path.join(root, "rust", "b200zk-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (b200zk_\w+)\(", sys_rs)) | set(re.findall(r"pub const (B200ZK_\w+):", sys_rs)) \
+        | set(re.findall(r"pub struct (b200zk_\w+) ", sys_rs))
+    header = open(os.path.join(root, "include", "b200zk.h")).read()
+    exported = set(re.findall(r"^(?:const\s+)?\w+\s*\*?\s*(b200zk_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S), flags=re.M))
+    assert exported and exported <= declared
+    shim = open(os.path.join(root, "rust", "b200zk", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(\w+)", shim))
+    assert used and used <= declared, sorted(used - declared)
