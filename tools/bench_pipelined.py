@@ -99,6 +99,7 @@ def main():
         same = all(np.array_equal(out[i], ref[i]) for i in range(K))
         print(json.dumps({"mode": "2 ctx, alternating full batches, stagger %.1f ms" % (delay * 1e3),
                           "proofs_per_s": B * K / tc, "ms_per_batch": tc / K * 1e3, "bit_exact_vs_1ctx": same}), flush=True)
+    pks[1]._h = None            # the second wrapper only borrows the key: pk frees it
 
 
 if __name__ == "__main__":
