@@ -65,7 +65,9 @@ int b200zk_sync(b200zk_ctx* ctx);
 /* options: "concurrency" (default 1): run the independent MSMs of a proof batch on auxiliary
  * streams; 0 serialises everything on the ctx stream (used for per-kernel profiling).
  * "msm_parts" (default 0 = automatic: 4 from 2^23 points, else 1): number of window groups a single
- * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream. */
+ * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream.
+ * "msm_glv" (default 1): G1 MSMs over plain bases split every scalar as k1 + k2*lambda (two non-negative
+ * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way. */
 int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value);
 /* raw device memory for callers that keep operands resident in HBM */
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** dptr);

@@ -5,6 +5,7 @@
 #include "../../zk-apps_b200/csrc/ec.cuh"
 #include "../../zk-apps_b200/csrc/pairing.cuh"
 #include "../../zk-apps_b200/csrc/verify.cuh"
+#include "../../zk-apps_b200/csrc/glv.cuh"
 #include <vector>
 using namespace b200zk;
 
@@ -125,5 +126,26 @@ int hc_verify(const uint8_t* vk_raw, uint32_t num_inputs, const uint8_t* proof, 
     PreparedVk pv;
     prepare_vk(alpha, g2s[0], g2s[1], g2s[2], pv);
     return verify_one(pv, abc.data(), num_inputs - 1, proof, x.data(), check_subgroup != 0);
+}
+// GLV (glv.cuh): k (n x 32 B canonical LE) -> k1, k2 (n x 20 B LE each)
+int hc_glv_split(const uint8_t* k, size_t n, uint8_t* k1, uint8_t* k2) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t kk[8], a[GLV_LIMBS], b[GLV_LIMBS];
+        memcpy(kk, k + i * 32, 32);
+        glv_split(kk, a, b);
+        memcpy(k1 + i * 4 * GLV_LIMBS, a, 4 * GLV_LIMBS);
+        memcpy(k2 + i * 4 * GLV_LIMBS, b, 4 * GLV_LIMBS);
+    }
+    return 0;
+}
+// phi(P) = (beta * x, y) for n affine G1 points (96 B, Montgomery)
+int hc_glv_phi(const uint8_t* in, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        Affine<Fq> p;
+        memcpy(&p, in + i * 96, 96);
+        p.x = fp_mul(p.x, glv_beta());
+        memcpy(out + i * 96, &p, 96);
+    }
+    return 0;
 }
 }

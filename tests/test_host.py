@@ -33,6 +33,8 @@ def hc(built):
     L.hc_field_op.argtypes = [C.c_int, C.c_int, vp, vp, vp, C.c_size_t]
     L.hc_msm_naive.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
     L.hc_madd_chain.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
+    L.hc_glv_split.argtypes = [vp, C.c_size_t, vp, vp]
+    L.hc_glv_phi.argtypes = [vp, C.c_size_t, vp]
     return L
 
 
@@ -132,8 +134,10 @@ def test_host_field_ops(hc, field):
             return np.frombuffer(b"".join(bls.fq_to_mont_bytes(v) for v in vals), dtype=np.uint8).copy()
         return np.frombuffer(b"".join(bls.fq_to_mont_bytes(v[0]) + bls.fq_to_mont_bytes(v[1]) for v in vals), dtype=np.uint8).copy()
     if field < 2:
-        A = [rnd.randrange(mod) for _ in range(n)] + [0, 1, mod - 1, mod - 1]
-        B = [rnd.randrange(mod) for _ in range(n)] + [mod - 1, mod - 1, mod - 1, 1]
+        edge = [2, 3, 4, mod - 2, (mod - 1) // 2, (mod + 1) // 2, 1 << 31, 1 << 32, 1 << 64, 1 << 200, (1 << 254) % mod,
+                (1 << 128) - 1, 0xFFFFFFFF, pow(2, -1, mod), pow(3, -1, mod)]            # inversion: binary-GCD corner cases
+        A = [rnd.randrange(mod) for _ in range(n)] + [0, 1, mod - 1, mod - 1] + edge
+        B = [rnd.randrange(mod) for _ in range(n)] + [mod - 1, mod - 1, mod - 1, 1] + edge[::-1]
         ops = {0: lambda x, y: (x + y) % mod, 1: lambda x, y: (x - y) % mod, 2: lambda x, y: x * y % mod,
                3: lambda x, y: x * x % mod, 4: lambda x, y: pow(x, -1, mod) if x else 0}
     else:
@@ -204,3 +208,30 @@ def test_rust_sys_bindings_match_header():
     shim = open(os.path.join(root, "rust", "b200zk", "src", "lib.rs")).read()
     used = set(re.findall(r"sys::(\w+)", shim))
     assert used and used <= declared, sorted(used - declared)
+
+
+def test_glv_split(hc):
+    """glv.cuh: k = k1 + k2 * lambda as INTEGERS with k1 < lambda, k2 = floor(k / lambda), for every 256-bit k (also
+    unreduced ones), and phi(P) = (beta x, y) = lambda * P on G1.  lambda = z^2 - 1, lambda^2 + lambda + 1 = r."""
+    zz = -0xd201000000010000
+    lam = zz * zz - 1
+    assert lam * lam + lam + 1 == R
+    rnd = random.Random(5)
+    ks = [0, 1, 2, lam - 1, lam, lam + 1, 2 * lam - 1, 2 * lam, R - 1, R - 2, R, (R - 1) // lam * lam, (R - 1) // lam * lam - 1,
+          (1 << 256) - 1, (1 << 255), (1 << 128) - 1, 1 << 128, lam * lam, lam * lam - 1, lam * (lam + 1)]
+    ks += [rnd.randrange(R) for _ in range(3000)] + [rnd.randrange(1 << 256) for _ in range(500)]
+    ks += [q * lam + d for q in (1, 7, lam // 3, lam, lam + 1) for d in (0, 1, lam - 1)]
+    buf = np.frombuffer(b"".join(bls.int_to_le(k, 32) for k in ks), dtype=np.uint8).copy()
+    k1 = np.zeros(len(ks) * 20, dtype=np.uint8)
+    k2 = np.zeros(len(ks) * 20, dtype=np.uint8)
+    hc.hc_glv_split(_p(buf), len(ks), _p(k1), _p(k2))
+    for i, k in enumerate(ks):
+        a = int.from_bytes(k1[i * 20:(i + 1) * 20].tobytes(), "little")
+        b = int.from_bytes(k2[i * 20:(i + 1) * 20].tobytes(), "little")
+        assert (a, b) == (k % lam, k // lam), hex(k)
+        assert a < (1 << 128) and b < (1 << 129)
+    pts = [bls.G1.mul(bls.G1.gen, s) for s in (1, 2, 12345, R - 1)]
+    enc = util.g1_array(pts)
+    out = np.zeros_like(enc)
+    hc.hc_glv_phi(_p(enc), len(pts), _p(out))
+    assert util.g1_list(out) == [bls.G1.mul(p, lam) for p in pts]

@@ -38,6 +38,7 @@ struct b200zk_ctx {
     cudaEvent_t ev_msm[3] = {nullptr, nullptr, nullptr};   // completion of the a / b_g1 / b_g2 MSMs
     bool concurrency = true;                               // b200zk_set_option("concurrency")
     int msm_parts = 0;                                     // b200zk_set_option("msm_parts"): 0 = automatic
+    bool msm_glv = true;                                   // b200zk_set_option("msm_glv"): GLV for plain G1 bases
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
     std::map<uint64_t, b200zk::DeviceBuf> tables;          // twiddle / coset tables, keyed

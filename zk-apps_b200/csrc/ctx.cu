@@ -72,6 +72,10 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
         ctx->msm_parts = value;
         return B200ZK_OK;
     }
+    if (strcmp(name, "msm_glv") == 0) {  // 1 (default): GLV half-length scalars for G1 MSMs over plain bases
+        ctx->msm_glv = value != 0;
+        return B200ZK_OK;
+    }
     return fail(ctx, B200ZK_ERR_BAD_ARG, std::string("unknown option ") + name);
 }
 

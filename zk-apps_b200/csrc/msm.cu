@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "glv.cuh"
 #include "types.cuh"
 
 using namespace b200zk;
@@ -36,21 +37,23 @@ struct Plan {
     uint32_t weff;                // bucket sets per msm: windows (of this part), or 1 when precomputed
     bool precomp;
     uint32_t w0, w1;              // windows [w0, w1) this pass of the pipeline handles (all of them unless split)
+    bool glv;                     // G1, plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
 };
 
 // Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
 // plus ~4 full additions (14 each) per bucket for the reduction; without precomputed window
 // multiples every window has its own bucket set.
-uint32_t pick_window(size_t n, bool precomp) {
+uint32_t pick_window(size_t n, bool precomp, bool glv) {
     if (const char* e = getenv(precomp ? "B200ZK_MSM_C_PRE" : "B200ZK_MSM_C")) {
         int v = atoi(e);
         if (v >= 2 && v <= 22) return (uint32_t)v;
     }
+    const uint32_t bits = glv ? GLV_BITS : 256;
     double best = 1e300;
     uint32_t best_c = 3;
     for (uint32_t c = 3; c <= 20; c++) {
-        const double W = (256 + c - 1) / c;
-        const double madds = (double)n * W * 10.0, per_set = (double)(1u << (c - 1)) * 56.0;
+        const double W = (bits + c - 1) / c;
+        const double madds = (double)n * (glv ? 2.0 : 1.0) * W * 10.0, per_set = (double)(1u << (c - 1)) * 56.0;
         const double cost = madds + (precomp ? per_set : per_set * W);
         if (cost < best) {
             best = cost;
@@ -60,10 +63,11 @@ uint32_t pick_window(size_t n, bool precomp) {
     return best_c;
 }
 
-Plan make_plan(size_t n, bool precomp, uint32_t c_fixed) {
+Plan make_plan(size_t n, bool precomp, uint32_t c_fixed, bool glv = false) {
     Plan p;
-    p.c = c_fixed ? c_fixed : pick_window(n, precomp);
-    p.windows = (256 + p.c - 1) / p.c;
+    p.glv = glv && !precomp;
+    p.c = c_fixed ? c_fixed : pick_window(n, precomp, p.glv);
+    p.windows = ((p.glv ? GLV_BITS : 256) + p.c - 1) / p.c;
     p.nb = 1u << (p.c - 1);
     p.precomp = precomp;
     p.weff = precomp ? 1 : p.windows;
@@ -102,43 +106,61 @@ __device__ __forceinline__ void load_scalar(const uint32_t* scalars, size_t idx,
     for (int i = 0; i < 8; i++) k[i] = s.v[i];
 }
 
-// scalars: batch rows of n scalars, row stride `stride` elements
-__global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
-                          const uint8_t* __restrict__ skip, uint32_t* counts) {
+// Calls f(key, entry) for every non-zero signed digit of scalar (b, i) that falls into the windows of this pass.
+// k: 8 limbs (upper ones zero for a GLV half scalar); pidx0: index of the base in window 0's table.
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const uint32_t* k, const Plan& pl, uint32_t b, size_t pidx0, size_t n, Fn f) {
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.windows; w++) {
+        int32_t d = next_digit(k, w, pl.c, carry);
+        if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
+        uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
+        uint32_t key = (b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
+        uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * n + pidx0 : pidx0);
+        f(key, pidx | (d < 0 ? 0x80000000u : 0u));
+    }
+}
+
+template <class Fn>
+__device__ __forceinline__ void for_each_entry(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont,
+                                               const Plan& pl, const uint8_t* __restrict__ skip, Fn f) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     const size_t b = t / n, i = t % n;
     if (skip && skip[i]) return;
     uint32_t k[8];
     load_scalar(scalars, b * stride + i, mont != 0, k);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < pl.windows; w++) {
-        int32_t d = next_digit(k, w, pl.c, carry);
-        if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
-        uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
-        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
-        atomicAdd(&counts[key], 1u);
+    if (pl.glv) {
+        uint32_t k1[8], k2[8];
+#pragma unroll
+        for (int j = GLV_LIMBS; j < 8; j++) k1[j] = k2[j] = 0;
+        glv_split(k, k1, k2);
+        for_each_digit(k1, pl, (uint32_t)b, i, n, f);
+        for_each_digit(k2, pl, (uint32_t)b, n + i, n, f);   // phi(P_i) lives at index n + i
+    } else {
+        for_each_digit(k, pl, (uint32_t)b, i, n, f);
     }
+}
+
+// scalars: batch rows of n scalars, row stride `stride` elements
+__global__ void msm_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
+                          const uint8_t* __restrict__ skip, uint32_t* counts) {
+    for_each_entry(scalars, n, stride, batch, mont, pl, skip, [&](uint32_t key, uint32_t) { atomicAdd(&counts[key], 1u); });
 }
 
 __global__ void msm_scatter(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, Plan pl,
                             const uint8_t* __restrict__ skip, uint32_t* cursor, uint32_t* sorted) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= n * batch) return;
-    const size_t b = t / n, i = t % n;
-    if (skip && skip[i]) return;
-    uint32_t k[8];
-    load_scalar(scalars, b * stride + i, mont != 0, k);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < pl.windows; w++) {
-        int32_t d = next_digit(k, w, pl.c, carry);
-        if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
-        uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
-        uint32_t key = ((uint32_t)b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
-        uint32_t pos = atomicAdd(&cursor[key], 1u);
-        uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * n + i : i);
-        sorted[pos] = pidx | (d < 0 ? 0x80000000u : 0u);
-    }
+    for_each_entry(scalars, n, stride, batch, mont, pl, skip,
+                   [&](uint32_t key, uint32_t entry) { sorted[atomicAdd(&cursor[key], 1u)] = entry; });
+}
+
+// second half of a GLV base table: phi(P) = (beta * x, y)
+__global__ void glv_phi_kernel(const Affine<Fq>* __restrict__ in, size_t n, Affine<Fq>* __restrict__ out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<Fq> p = in[i];
+    p.x = fp_mul(p.x, glv_beta());
+    out[i] = p;
 }
 
 // ---------------------------------------------------------------- exclusive scan (3 kernels)
@@ -262,6 +284,7 @@ __device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_
 
 template <class F, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F>* __restrict__ bases,
+                                                      const Affine<F>* __restrict__ bases2, uint32_t n_split,
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ soff, uint32_t n_keys,
@@ -284,8 +307,13 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
     uint32_t key = lo;
     uint32_t bend = offsets[key + 1];
     XYZZ<F> acc = XYZZ<F>::inf();
+    // entries below n_split index `bases`, the others `bases2` (the phi half of a GLV table)
+    auto base_ptr = [&](uint32_t e) {
+        const uint32_t idx = e & 0x7fffffffu;
+        return idx < n_split ? bases + idx : bases2 + (idx - n_split);
+    };
     uint32_t v = sorted[k];
-    Affine<F> cur = load_affine(bases + (v & 0x7fffffffu));
+    Affine<F> cur = load_affine(base_ptr(v));
     bool neg = (v >> 31) != 0;
     // G1: the next point is loaded into registers while the current addition runs.  G2: accumulator (96
     // registers) + current point (48) + a second point (48) do not fit in 255 registers next to the formula's
@@ -298,7 +326,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         uint32_t vn = 0;
         if (kn < end) {
             vn = sorted[kn];
-            const Affine<F>* np = bases + (vn & 0x7fffffffu);
+            const Affine<F>* np = base_ptr(vn);
             if constexpr (PREFETCH_TO_REGS) {
                 nxt = load_affine(np);  // in flight during the add
             } else {
@@ -318,7 +346,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
             } while (bend == kn);
         }
         if constexpr (PREFETCH_TO_REGS) cur = nxt;
-        else cur = load_affine(bases + (vn & 0x7fffffffu));
+        else cur = load_affine(base_ptr(vn));
         neg = (vn >> 31) != 0;
         k = kn;
     }
@@ -577,13 +605,14 @@ namespace b200zk {
 // stream of `slot`, with that slot's scratch buffers.  *sums_out: device array [batch][pl.weff] of window sums.
 template <class F>
 int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, size_t n, size_t stride, size_t batch,
-             bool mont, const Plan& pl, int slot, const XYZZ<F>** sums_out) {
+             bool mont, const Plan& pl, int slot, const Affine<F>* d_phi, const XYZZ<F>** sums_out) {
     const cudaStream_t st = slot_stream(ctx, slot);
     if (!ctx->concurrency) slot = 0;
     const uint32_t part_windows = pl.w1 - pl.w0;
     const uint64_t n_keys64 = (uint64_t)batch * pl.weff * pl.nb;
-    const uint64_t max_entries = (uint64_t)batch * n * part_windows;
-    if (n_keys64 >= (1ull << 31) || max_entries >= (1ull << 32) || (uint64_t)h->n * pl.windows >= (1ull << 31))
+    const uint64_t max_entries = (uint64_t)batch * n * part_windows * (pl.glv ? 2 : 1);
+    if (n_keys64 >= (1ull << 31) || max_entries >= (1ull << 32) || (uint64_t)h->n * pl.windows >= (1ull << 31) ||
+        (pl.glv && 2 * (uint64_t)n >= (1ull << 31)))
         return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit bucket keys; split the batch");
     const uint32_t n_keys = (uint32_t)n_keys64;
 
@@ -646,7 +675,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
         const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;
         kern<<<div_up(max_runs, acc_threads), acc_threads, 0, st>>>(
-            (const Affine<F>*)h->d_points, (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
+            (const Affine<F>*)h->d_points, d_phi, pl.glv ? (uint32_t)n : 0x80000000u, (const uint32_t*)d_offsets,
+            (const uint32_t*)d_sorted,
             (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
     }
@@ -721,7 +751,20 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), st));
         return B200ZK_OK;
     }
-    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0);
+    // plain G1 bases: GLV halves the scalar length (glv.cuh); the phi half of the table is rebuilt per call
+    // (n products, one pass over the points) so the handle stays a plain array of the caller's bases
+    const bool glv = sizeof(F) == sizeof(Fq) && !h->precomputed && ctx->msm_glv && n >= 2;
+    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0, glv);
+    const Affine<F>* d_phi = nullptr;
+    if constexpr (sizeof(F) == sizeof(Fq)) {
+        if (pl.glv) {
+            void* ph;
+            B200ZK_TRY(scratch(ctx, "msm_glv_phi", n * sizeof(Affine<Fq>), &ph, ctx->concurrency ? slot : 0));
+            glv_phi_kernel<<<div_up(n, 128), 128, 0, st>>>((const Affine<Fq>*)h->d_points, n, (Affine<Fq>*)ph);
+            B200ZK_TRY(check_launch(ctx, "glv_phi_kernel"));
+            d_phi = (const Affine<F>*)ph;
+        }
+    }
     uint32_t parts = 1;
     if (!pl.precomp && batch == 1 && slot == 0 && ctx->concurrency) {
         if (ctx->msm_parts) parts = (uint32_t)ctx->msm_parts;
@@ -730,7 +773,7 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     parts = std::min(parts, pl.windows);
     const XYZZ<F>* sums = nullptr;
     if (parts == 1) {
-        B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pl, slot, &sums));
+        B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pl, slot, d_phi, &sums));
     } else {
         static const int part_slot[4] = {0, 5, 6, 8};   // streams: main, aux[0], aux[1], aux[3] (priority order)
         void* d_ws;
@@ -746,7 +789,7 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
             const cudaStream_t ps = slot_stream(ctx, part_slot[i]);
             if (i) B200ZK_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->ev_fork, 0));
             const XYZZ<F>* part_sums = nullptr;
-            B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pp, part_slot[i], &part_sums));
+            B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pp, part_slot[i], d_phi, &part_sums));
             B200ZK_CUDA(ctx, cudaMemcpyAsync((XYZZ<F>*)d_ws + pp.w0, part_sums, (size_t)pp.weff * sizeof(XYZZ<F>),
                                              cudaMemcpyDeviceToDevice, ps));
             if (i) {
