@@ -12,8 +12,12 @@ ap.add_argument("--msm-g2", default="16")
 ap.add_argument("--ntt", default="16,20,22,24")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--precompute", type=int, default=0)
+ap.add_argument("--parts", type=int, default=0, help="msm_parts option (0 = automatic)")
+ap.add_argument("--glv", type=int, default=1, help="msm_glv option")
 args = ap.parse_args()
 ctx = z.Context(0)
+ctx.set_option("msm_parts", args.parts)
+ctx.set_option("msm_glv", args.glv)
 res = {"msm": [], "ntt": []}
 
 def rand_scalars(n, seed):

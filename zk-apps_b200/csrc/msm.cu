@@ -639,7 +639,11 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     }
     // runs of L = 2^log_tl entries; smaller L when the problem is small, to keep the SMs busy
     void *d_tcount, *d_toff, *d_partials, *d_big;
+    // ... and longer runs when the buckets are large (run ~ half the mean bucket), so that a bucket still
+    // spans only ~3 runs: with 64-entry runs a 2^26-point GLV MSM (512 entries per bucket) sent every bucket,
+    // 9 partials each, to the warp-per-bucket fold (129 ms instead of 6)
     uint32_t log_tl = 6;
+    while (log_tl < 10 && (max_entries / n_keys) >= (4ull << log_tl)) log_tl++;
     while (log_tl > 3 && (max_entries >> log_tl) < 65536) log_tl--;
     const uint64_t max_runs = (max_entries >> log_tl) + 1;
     const uint64_t max_segs = (uint64_t)n_keys + max_runs + 1;
