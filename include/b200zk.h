@@ -66,7 +66,7 @@ int b200zk_sync(b200zk_ctx* ctx);
  * streams; 0 serialises everything on the ctx stream (used for per-kernel profiling).
  * "msm_parts" (default 0 = automatic: 4 from 2^23 points, else 1): number of window groups a single
  * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream.
- * "msm_glv" (default 1): G1 MSMs over plain bases split every scalar as k1 + k2*lambda (two non-negative
+ * "msm_glv" (default 1): MSMs (G1 and G2) over plain bases split every scalar as k1 + k2*lambda (two non-negative
  * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way. */
 int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value);
 /* raw device memory for callers that keep operands resident in HBM */

@@ -138,13 +138,20 @@ int hc_glv_split(const uint8_t* k, size_t n, uint8_t* k1, uint8_t* k2) {
     }
     return 0;
 }
-// phi(P) = (beta * x, y) for n affine G1 points (96 B, Montgomery)
-int hc_glv_phi(const uint8_t* in, size_t n, uint8_t* out) {
+// phi(P) = (beta x, y) for n affine points (G1: 96 B, G2: 192 B, Montgomery)
+int hc_glv_phi(int group, const uint8_t* in, size_t n, uint8_t* out) {
     for (size_t i = 0; i < n; i++) {
-        Affine<Fq> p;
-        memcpy(&p, in + i * 96, 96);
-        p.x = fp_mul(p.x, glv_beta());
-        memcpy(out + i * 96, &p, 96);
+        if (group == 1) {
+            Affine<Fq> p;
+            memcpy(&p, in + i * 96, 96);
+            p.x = glv_phi_x(p.x);
+            memcpy(out + i * 96, &p, 96);
+        } else {
+            Affine<Fq2> p;
+            memcpy(&p, in + i * 192, 192);
+            p.x = glv_phi_x(p.x);
+            memcpy(out + i * 192, &p, 192);
+        }
     }
     return 0;
 }

@@ -34,7 +34,7 @@ def hc(built):
     L.hc_msm_naive.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
     L.hc_madd_chain.argtypes = [C.c_int, vp, vp, C.c_size_t, vp]
     L.hc_glv_split.argtypes = [vp, C.c_size_t, vp, vp]
-    L.hc_glv_phi.argtypes = [vp, C.c_size_t, vp]
+    L.hc_glv_phi.argtypes = [C.c_int, vp, C.c_size_t, vp]
     return L
 
 
@@ -212,7 +212,7 @@ def test_rust_sys_bindings_match_header():
 
 def test_glv_split(hc):
     """glv.cuh: k = k1 + k2 * lambda as INTEGERS with k1 < lambda, k2 = floor(k / lambda), for every 256-bit k (also
-    unreduced ones), and phi(P) = (beta x, y) = lambda * P on G1.  lambda = z^2 - 1, lambda^2 + lambda + 1 = r."""
+    unreduced ones), and phi(P) = (beta x, y) = lambda * P on G1 (beta^2 on G2).  lambda = z^2 - 1, lambda^2 + lambda + 1 = r."""
     zz = -0xd201000000010000
     lam = zz * zz - 1
     assert lam * lam + lam + 1 == R
@@ -230,8 +230,9 @@ def test_glv_split(hc):
         b = int.from_bytes(k2[i * 20:(i + 1) * 20].tobytes(), "little")
         assert (a, b) == (k % lam, k // lam), hex(k)
         assert a < (1 << 128) and b < (1 << 129)
-    pts = [bls.G1.mul(bls.G1.gen, s) for s in (1, 2, 12345, R - 1)]
-    enc = util.g1_array(pts)
-    out = np.zeros_like(enc)
-    hc.hc_glv_phi(_p(enc), len(pts), _p(out))
-    assert util.g1_list(out) == [bls.G1.mul(p, lam) for p in pts]
+    for group, cv, enc_fn, dec_fn in ((1, bls.G1, util.g1_array, util.g1_list), (2, bls.G2, util.g2_array, util.g2_list)):
+        pts = [cv.mul(cv.gen, s) for s in (1, 2, 12345, R - 1)]
+        enc = enc_fn(pts)
+        out = np.zeros_like(enc)
+        hc.hc_glv_phi(group, _p(enc), len(pts), _p(out))
+        assert dec_fn(out) == [cv.mul(p, lam) for p in pts]

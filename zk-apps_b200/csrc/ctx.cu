@@ -72,7 +72,7 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
         ctx->msm_parts = value;
         return B200ZK_OK;
     }
-    if (strcmp(name, "msm_glv") == 0) {  // 1 (default): GLV half-length scalars for G1 MSMs over plain bases
+    if (strcmp(name, "msm_glv") == 0) {  // 1 (default): GLV half-length scalars for MSMs over plain bases
         ctx->msm_glv = value != 0;
         return B200ZK_OK;
     }

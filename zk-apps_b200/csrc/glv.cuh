@@ -1,8 +1,8 @@
-// GLV decomposition for G1 of BLS12-381 (used by plain-bases MSMs, msm.cu).
+// GLV decomposition for G1 and G2 of BLS12-381 (used by plain-bases MSMs, msm.cu).
 //
 // With z = -0xd201000000010000, lambda = z^2 - 1 satisfies lambda^2 + lambda + 1 = r EXACTLY (not only mod r),
 // and phi(x, y) = (beta * x, y), beta a primitive cube root of unity in Fq, acts on G1 as multiplication by
-// lambda.  So the integer identity  k = k1 + k2 * lambda,  k2 = floor(k / lambda),  k1 = k mod lambda  gives
+// lambda (on G2, over the twist, the root with that eigenvalue is beta^2).  So the integer identity  k = k1 + k2 * lambda,  k2 = floor(k / lambda),  k1 = k mod lambda  gives
 // k * P = k1 * P + k2 * phi(P)  with two NON-NEGATIVE half-length scalars (k1 < lambda < 2^128,
 // k2 <= floor((2^256 - 1) / lambda) < 2^129): half the windows, half the bucket sets and half the doublings of
 // the Horner step for twice the (cheap) bucket entries per window.  Constants derived and checked with the
@@ -26,6 +26,18 @@ HD Fq glv_beta() {                  // beta * 2^384 mod p: phi(G) = lambda * G w
     Fq b = {{0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu, 0x01bacb9eu,
              0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u}};
     return b;
+}
+
+HD Fq glv_beta_g2() {               // beta^2: on the twist E'(Fq2) it is (beta^2 x, y) that acts on G2 as lambda
+    Fq b = {{0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au, 0x74fd029bu,
+             0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu}};
+    return b;
+}
+// x-coordinate of phi(P) = lambda * P
+HD Fq glv_phi_x(const Fq& x) { return fp_mul(x, glv_beta()); }
+HD Fq2 glv_phi_x(const Fq2& x) {
+    const Fq b = glv_beta_g2();
+    return Fq2{fp_mul(x.c0, b), fp_mul(x.c1, b)};
 }
 
 constexpr int GLV_LIMBS = 5;   // limbs of a half scalar

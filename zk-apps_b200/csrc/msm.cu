@@ -37,7 +37,7 @@ struct Plan {
     uint32_t weff;                // bucket sets per msm: windows (of this part), or 1 when precomputed
     bool precomp;
     uint32_t w0, w1;              // windows [w0, w1) this pass of the pipeline handles (all of them unless split)
-    bool glv;                     // G1, plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
+    bool glv;                     // plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
 };
 
 // Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
@@ -154,12 +154,13 @@ __global__ void msm_scatter(const uint32_t* scalars, size_t n, size_t stride, si
                    [&](uint32_t key, uint32_t entry) { sorted[atomicAdd(&cursor[key], 1u)] = entry; });
 }
 
-// second half of a GLV base table: phi(P) = (beta * x, y)
-__global__ void glv_phi_kernel(const Affine<Fq>* __restrict__ in, size_t n, Affine<Fq>* __restrict__ out) {
+// second half of a GLV base table: phi(P) = (beta * x, y)   (beta^2 on G2)
+template <class F>
+__global__ void glv_phi_kernel(const Affine<F>* __restrict__ in, size_t n, Affine<F>* __restrict__ out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Affine<Fq> p = in[i];
-    p.x = fp_mul(p.x, glv_beta());
+    Affine<F> p = in[i];
+    p.x = glv_phi_x(p.x);
     out[i] = p;
 }
 
@@ -755,19 +756,18 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_out, 0, batch * sizeof(Affine<F>), st));
         return B200ZK_OK;
     }
-    // plain G1 bases: GLV halves the scalar length (glv.cuh); the phi half of the table is rebuilt per call
+    // plain bases: GLV halves the scalar length (glv.cuh); the phi half of the table is rebuilt per call
     // (n products, one pass over the points) so the handle stays a plain array of the caller's bases
-    const bool glv = sizeof(F) == sizeof(Fq) && !h->precomputed && ctx->msm_glv && n >= 2;
+    const bool glv = !h->precomputed && ctx->msm_glv && n >= 2;
     Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0, glv);
     const Affine<F>* d_phi = nullptr;
-    if constexpr (sizeof(F) == sizeof(Fq)) {
-        if (pl.glv) {
-            void* ph;
-            B200ZK_TRY(scratch(ctx, "msm_glv_phi", n * sizeof(Affine<Fq>), &ph, ctx->concurrency ? slot : 0));
-            glv_phi_kernel<<<div_up(n, 128), 128, 0, st>>>((const Affine<Fq>*)h->d_points, n, (Affine<Fq>*)ph);
-            B200ZK_TRY(check_launch(ctx, "glv_phi_kernel"));
-            d_phi = (const Affine<F>*)ph;
-        }
+    if (pl.glv) {
+        void* ph;
+        B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_glv_phi_g1" : "msm_glv_phi_g2", n * sizeof(Affine<F>), &ph,
+                           ctx->concurrency ? slot : 0));
+        glv_phi_kernel<F><<<div_up(n, 128), 128, 0, st>>>((const Affine<F>*)h->d_points, n, (Affine<F>*)ph);
+        B200ZK_TRY(check_launch(ctx, "glv_phi_kernel"));
+        d_phi = (const Affine<F>*)ph;
     }
     uint32_t parts = 1;
     if (!pl.precomp && batch == 1 && slot == 0 && ctx->concurrency) {
