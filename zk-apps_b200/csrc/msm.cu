@@ -679,7 +679,11 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         // CTA width (<= 128): narrower CTAs leave registers for latency-bound CTAs of other MSMs (experiments)
         static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
         const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;
-        kern<<<div_up(max_runs, acc_threads), acc_threads, 0, st>>>(
+        // experiments: a dynamic shared-memory request caps the resident CTAs per SM independently of the register
+        // budget the kernel was compiled for (B200ZK_ACC_BLOCKS=3 -> 168 registers, B200ZK_ACC_SMEM_KB=100 -> 2 CTAs)
+        static const int smem_kb = getenv("B200ZK_ACC_SMEM_KB") ? atoi(getenv("B200ZK_ACC_SMEM_KB")) : 0;
+        if (smem_kb > 0) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
+        kern<<<div_up(max_runs, acc_threads), acc_threads, (size_t)smem_kb * 1024, st>>>(
             (const Affine<F>*)h->d_points, d_phi, pl.glv ? (uint32_t)n : 0x80000000u, (const uint32_t*)d_offsets,
             (const uint32_t*)d_sorted,
             (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
