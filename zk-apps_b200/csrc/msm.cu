@@ -718,11 +718,10 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)sets + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
     {
         ProfScope ps(ctx, "msm_reduce", st);
-        static bool attr_done[2] = {false, false};
-        if (!attr_done[sizeof(F) == sizeof(Fq) ? 0 : 1]) {
+        if (red_smem > 48 * 1024) {  // per device and per function, so set on every call (a few hundred ns): no
+                                     // process-wide "done" flag that a second device or a second thread could trip over
             B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_seg_reduce<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
             B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_seg_combine<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-            attr_done[sizeof(F) == sizeof(Fq) ? 0 : 1] = true;
         }
         XYZZ<F>* Wseg = (XYZZ<F>*)d_red_a;
         XYZZ<F>* Rseg = Wseg + (size_t)sets * segs;

@@ -199,11 +199,36 @@ HD_NOINLINE Fq12 miller_loop(const Affine<Fq>& p, const Affine<Fq2>& q) {
 }
 
 // ------------------------------------------------------------------ final exponentiation
+// Squaring in the cyclotomic subgroup (Granger-Scott; the form ark-ff 0.4 uses in Fp12::cyclotomic_square
+// [recall]): with a = (z0, z1), b = (z2, z3), c = (z4, z5) in Fq4 = Fq2[y]/(y^2 - xi), three Fq4 squarings of two
+// Fq2 products each -- 18 Fq products instead of the 36 of fq12_sqr.  Valid after the easy part only.
+HD_NOINLINE Fq12 fq12_cyclotomic_sqr(const Fq12& f) {
+    const Fq2 &z0 = f.c0.c0, &z4 = f.c0.c1, &z3 = f.c0.c2, &z2 = f.c1.c0, &z1 = f.c1.c1, &z5 = f.c1.c2;
+    Fq2 tmp = fp_mul(z0, z1);
+    const Fq2 t0 = fp_sub(fp_sub(fp_mul(fp_add(z0, z1), fp_add(fq2_mul_by_xi(z1), z0)), tmp), fq2_mul_by_xi(tmp));
+    const Fq2 t1 = fp_dbl(tmp);
+    tmp = fp_mul(z2, z3);
+    const Fq2 t2 = fp_sub(fp_sub(fp_mul(fp_add(z2, z3), fp_add(fq2_mul_by_xi(z3), z2)), tmp), fq2_mul_by_xi(tmp));
+    const Fq2 t3 = fp_dbl(tmp);
+    tmp = fp_mul(z4, z5);
+    const Fq2 t4 = fp_sub(fp_sub(fp_mul(fp_add(z4, z5), fp_add(fq2_mul_by_xi(z5), z4)), tmp), fq2_mul_by_xi(tmp));
+    const Fq2 t5 = fp_dbl(tmp);
+    Fq12 r;
+    r.c0.c0 = fp_add(fp_dbl(fp_sub(t0, z0)), t0);        // 3 t0 - 2 z0
+    r.c1.c1 = fp_add(fp_dbl(fp_add(t1, z1)), t1);        // 3 t1 + 2 z1
+    tmp = fq2_mul_by_xi(t5);
+    r.c1.c0 = fp_add(fp_dbl(fp_add(tmp, z2)), tmp);      // 3 xi t5 + 2 z2
+    r.c0.c2 = fp_add(fp_dbl(fp_sub(t4, z3)), t4);        // 3 t4 - 2 z3
+    r.c0.c1 = fp_add(fp_dbl(fp_sub(t2, z4)), t2);        // 3 t2 - 2 z4
+    r.c1.c2 = fp_add(fp_dbl(fp_add(t3, z5)), t3);        // 3 t3 + 2 z5
+    return r;
+}
+
 // f^x for a cyclotomic f (x = -BLS_X_ABS: power by |x|, then conjugate = inverse)
 HD_NOINLINE Fq12 fq12_exp_by_x(const Fq12& f) {
     Fq12 r = f;
     for (int bit = 62; bit >= 0; bit--) {
-        r = fq12_sqr(r);
+        r = fq12_cyclotomic_sqr(r);
         if ((BLS_X_ABS >> bit) & 1) r = fq12_mul(r, f);
     }
     return fq12_conj(r);
@@ -214,7 +239,7 @@ HD_NOINLINE Fq12 final_exponentiation(const Fq12& f) {
     Fq12 r = fq12_mul(fq12_conj(f), fq12_inv(f));
     r = fq12_mul(fq12_frob(fq12_frob(r)), r);
     // hard part: r^((x-1)^2 (x+p) (x^2+p^2-1) + 3)
-    Fq12 y0 = fq12_sqr(r);
+    Fq12 y0 = fq12_cyclotomic_sqr(r);
     Fq12 y1 = fq12_exp_by_x(r);
     Fq12 y2 = fq12_conj(r);
     y1 = fq12_mul(y1, y2);                 // r^(x-1)
