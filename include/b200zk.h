@@ -277,7 +277,8 @@ int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, 
  * b200zk_groth16_verify_batch: proofs = batch * 192 B compressed A|B|C; public_inputs = batch *
  *   (num_inputs-1) * 32 B Montgomery Fr (ark `&[Fr]`, the ONE is implicit); both host or both device.
  *   status_out (host, one per proof) receives a b200zk_proof_status: never an aggregate verdict.
- *   check_subgroup != 0 also tests [r]P = O on A, B, C (ark Validate::Yes on deserialisation).
+ *   check_subgroup != 0 also tests subgroup membership of A, B, C (ark Validate::Yes on deserialisation): the
+ *   endomorphism tests phi(P) == [z^2 - 1]P (G1) and psi(P) == [z]P (G2), equivalent to [r]P = O.
  * b200zk_groth16_verify_aggregate: ONE verdict for the whole batch from a random linear combination
  *   (prod e(r_i A_i, B_i) = e(alpha,beta)^(sum r_i) e(sum r_i L_i, gamma) e(sum r_i C_i, delta)): batch + 3
  *   Miller loops and one final exponentiation instead of 3 * batch and batch.  coeffs = batch * 16 B

@@ -111,6 +111,10 @@ int hc_compress(int group, const uint8_t* in, uint8_t* out) {
     if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); g1_compress(p, out); return 0; }
     Affine<Fq2> p; memcpy(&p, in, sizeof(p)); g2_compress(p, out); return 0;
 }
+int hc_in_subgroup_plain(int group, const uint8_t* in) {   // [r]P == O
+    if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g1_b()) && ec_in_subgroup_plain(p); }
+    Affine<Fq2> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g2_b()) && ec_in_subgroup_plain(p);
+}
 int hc_in_subgroup(int group, const uint8_t* in) {
     if (group == 1) { Affine<Fq> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g1_b()) && ec_in_subgroup(p); }
     Affine<Fq2> p; memcpy(&p, in, sizeof(p)); return ec_on_curve(p, g2_b()) && ec_in_subgroup(p);

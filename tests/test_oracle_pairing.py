@@ -140,3 +140,32 @@ def test_wire_format_roundtrip(hc):
             break
         x += 1
     assert hc.hc_in_subgroup(1, _p(np.frombuffer(bls.g1_to_ffi((x, y)), dtype=np.uint8).copy())) == 0
+
+
+def test_fast_subgroup_checks_agree_with_plain(hc):
+    """ec_in_subgroup (endomorphism tests: phi(P) == [z^2 - 1]P on G1, psi(P) == [z]P on G2) against [r]P == O, the
+    plain test, and against the oracle: subgroup points, random curve points (cofactor != 1, so almost surely
+    outside), pure cofactor-torsion points [r]Q, and sums of a subgroup point with a torsion point."""
+    import random
+    rnd = random.Random(11)
+    for group, cv, to_ffi in ((1, bls.G1, bls.g1_to_ffi), (2, bls.G2, bls.g2_to_ffi)):
+        def curve_point():
+            while True:
+                if group == 1:
+                    x = rnd.randrange(bls.P)
+                    y = bls.fq_sqrt((x * x * x + 4) % bls.P)
+                else:
+                    x = (rnd.randrange(bls.P), rnd.randrange(bls.P))
+                    y = bls.fq2_sqrt(bls.fq2_add(bls.fq2_mul(bls.fq2_sqr(x), x), (4, 4)))
+                if y is not None:
+                    return (x, y)
+        pts = [cv.mul(cv.gen, rnd.randrange(1, bls.R)) for _ in range(4)]
+        outside = [curve_point() for _ in range(4)]
+        torsion = [cv.mul(q, bls.R) for q in outside[:2]]                      # order divides the cofactor
+        mixed = [cv.add(pts[0], t) for t in torsion if t is not None]
+        for pt in pts + outside + [t for t in torsion if t is not None] + mixed:
+            want = 1 if cv.mul(pt, bls.R) is None else 0
+            buf = np.frombuffer(to_ffi(pt), dtype=np.uint8).copy()
+            assert hc.hc_in_subgroup_plain(group, _p(buf)) == want
+            assert hc.hc_in_subgroup(group, _p(buf)) == want, (group, pt)
+        assert sum(1 for pt in outside if cv.mul(pt, bls.R) is not None) >= 3    # the negative cases are real

@@ -21,6 +21,7 @@
 #pragma once
 #include "ec.cuh"
 #include "pairing_consts.cuh"
+#include "glv.cuh"
 
 namespace b200zk {
 
@@ -408,13 +409,48 @@ HD_NOINLINE void g2_compress(const Affine<Fq2>& p, uint8_t* b) {
     b[0] |= 0x80 | (fq2_lex_largest(p.y) ? 0x20 : 0);
 }
 
-// [r]P == O  (the plain subgroup test; r = the Fr modulus)
+// [r]P == O: the plain subgroup test (r = the Fr modulus), kept as the independent check of the fast tests below
 template <class F>
-HD_NOINLINE bool ec_in_subgroup(const Affine<F>& p) {
+HD_NOINLINE bool ec_in_subgroup_plain(const Affine<F>& p) {
     if (p.is_inf()) return true;
     uint32_t r[8];
     for (int i = 0; i < 8; i++) r[i] = FrCfg::mod(i);
     return ec_mul_scalar(XYZZ<F>::from_affine(p), r).is_inf();
+}
+
+// same point? (XYZZ representatives are not unique)
+template <class F>
+HD bool ec_same_point(const XYZZ<F>& a, const XYZZ<F>& b) {
+    if (a.is_inf() || b.is_inf()) return a.is_inf() && b.is_inf();
+    return fp_mul(a.x, b.zz) == fp_mul(b.x, a.zz) && fp_mul(a.y, b.zzz) == fp_mul(b.y, a.zzz);
+}
+
+template <class F>
+HD XYZZ<F> ec_mul_by_x_abs(const XYZZ<F>& p) {  // |z| * p, z = the curve parameter (64 bits, weight 6)
+    const uint32_t k[2] = {(uint32_t)BLS_X_ABS, (uint32_t)(BLS_X_ABS >> 32)};
+    return ec_mul_scalar(p, k, 2);
+}
+
+// Subgroup membership through the endomorphisms (Bowe 2019, Scott 2021): two / one multiplications by the 64-bit
+// curve parameter instead of one by the 255-bit r.
+//   G1: phi(P) = (beta x, y) has eigenvalue lambda = z^2 - 1 on G1 and lambda^2 + lambda + 1 = r as integers, so
+//       phi(P) == [z^2 - 1] P  implies  0 = (phi^2 + phi + 1) P = [r] P, and conversely holds on G1.
+//   G2: psi = twist o Frobenius o untwist has eigenvalue z on G2; psi(P) == [z] P characterises G2 (Scott,
+//       "A note on group membership tests for G1, G2 and GT on BLS pairing-friendly curves", section 4).
+// Both are pinned against the plain test, on subgroup points and on curve points outside it (tests/test_host.py).
+HD_NOINLINE bool ec_in_subgroup(const Affine<Fq>& p) {
+    if (p.is_inf()) return true;
+    const XYZZ<Fq> P = XYZZ<Fq>::from_affine(p);
+    XYZZ<Fq> q = ec_mul_by_x_abs(ec_mul_by_x_abs(P));   // [z^2] P (the two signs cancel)
+    ec_madd(q, p, true);                                // [z^2 - 1] P
+    return ec_same_point(q, XYZZ<Fq>::from_affine(Affine<Fq>{glv_phi_x(p.x), p.y}));
+}
+HD_NOINLINE bool ec_in_subgroup(const Affine<Fq2>& p) {
+    if (p.is_inf()) return true;
+    using namespace pairing_consts;
+    const XYZZ<Fq2> q = ec_neg(ec_mul_by_x_abs(XYZZ<Fq2>::from_affine(p)));   // [z] P, z < 0
+    const Affine<Fq2> psi{fp_mul(fq2_conj(p.x), psi_cx()), fp_mul(fq2_conj(p.y), psi_cy())};
+    return ec_same_point(q, XYZZ<Fq2>::from_affine(psi));
 }
 
 template <class F>
