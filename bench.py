@@ -377,7 +377,17 @@ def run_b200(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     extras = {}
     if world == 1 and not args.no_extras:
+        # BASELINE.json configs[1] / [2] as stated: ONE withdraw proof (G1 and G2 MSM paths) on one B200 -- latency
+        # of the user-facing call with host buffers, best of 5 after one warm-up at this batch size
+        one_in = pinned_in[0].numpy()[:in_bytes // B]
+        z.Groth16.prove_update_note(pk, one_in, rb[:32], sb[:32], 1)
+        lat = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            z.Groth16.prove_update_note(pk, one_in, rb[:32], sb[:32], 1)
+            lat.append((time.perf_counter() - t0) * 1e3)
         extras = extras_single_gpu(ctx, z, hbm_peak)
+        extras["single_proof_latency_ms"] = min(lat)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (Fr 255-bit, Fq 381-bit Montgomery)", "data": "synthetic",
