@@ -140,3 +140,38 @@ def test_window_group_parts(ctx, group, log_n, parts):
         h.free()
     assert not inf and dec(out)[0] == want
     assert bytes(out) == bytes(one) == bytes(out_again)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_glv_path_equals_full_length_path(ctx, group):
+    """b200zk_set_option "msm_glv": plain-bases MSMs split every scalar as k1 + k2*lambda (glv.cuh).  Same bytes as the
+    full-length path and as the oracle, on random scalars and on the decomposition's corner cases (0, 1, lambda +- 1,
+    multiples of lambda, r - 1), also batched."""
+    cv, enc, dec, pt = CURVES[group]
+    zz = -0xd201000000010000
+    lam = zz * zz - 1
+    corner = [0, 1, 2, lam - 1, lam, lam + 1, 2 * lam, lam * lam % R, (R - 1) // lam * lam, R - 1, R - 2, (1 << 128) - 1, 1 << 128,
+              1 << 254]
+    n = 256
+    ks, pts = _gpu_bases(ctx, group, 500 + group, n)
+    scal = corner + util.le_ints(util.rand_fr_bytes_fast(600 + group, n - len(corner)))
+    sbuf = util.scalars_array(scal)
+    want = cv.mul(cv.gen, sum(a * b for a, b in zip(ks, scal)) % R)
+    h = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=False)
+    try:
+        outs = {}
+        for glv in (0, 1):
+            ctx.set_option("msm_glv", glv)
+            outs[glv] = (h.msm(sbuf)[0], h.msm(np.concatenate([sbuf, util.scalars_array(scal[::-1])]), n=n, batch=2)[0],
+                         z.VariableBaseMSM.msm_bigint(ctx, group, pts, sbuf)[0])
+    finally:
+        ctx.set_option("msm_glv", 1)
+        h.free()
+    assert dec(outs[1][0])[0] == want
+    assert bytes(outs[0][0]) == bytes(outs[1][0]) and bytes(outs[0][1]) == bytes(outs[1][1])
+    assert bytes(outs[0][2]) == bytes(outs[1][2]) == bytes(outs[1][0])
+    # every scalar a corner case at once (all lanes take the same path)
+    for s in (lam, lam - 1, R - 1):
+        ctx.set_option("msm_glv", 1)
+        out, _ = z.VariableBaseMSM.msm_bigint(ctx, group, pts, util.scalars_array([s] * n))
+        assert dec(out)[0] == cv.mul(cv.gen, sum(ks) % R * s % R)
