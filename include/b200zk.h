@@ -55,7 +55,8 @@ typedef enum {
 
 enum { B200ZK_FIELD_FR = 0, B200ZK_FIELD_FQ = 1, B200ZK_FIELD_FQ2 = 2 };
 enum { B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQR = 3, B200ZK_OP_INV = 4,
-       B200ZK_OP_TO_MONT = 5, B200ZK_OP_FROM_MONT = 6 };
+       B200ZK_OP_TO_MONT = 5, B200ZK_OP_FROM_MONT = 6,
+       B200ZK_OP_MUL_DFMA = 7 /* experiment: Fq product on the FP64 pipe (csrc/field_dfma.cuh); Fq only */ };
 
 /* ---- context ------------------------------------------------------------------------- */
 int b200zk_init(int device, b200zk_ctx** out);
@@ -100,7 +101,9 @@ int b200zk_stat_reset(b200zk_ctx* ctx);
 int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b,
                         uint8_t* out, size_t n);
 /* Integer-pipe micro-benchmarks: kind 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (mad.wide), 2 = Fr
- * Montgomery mul, 3 = Fq Montgomery mul, 4 = DFMA.  Returns operations (IMADs, or field muls) per
+ * Montgomery mul, 3 = Fq Montgomery mul, 4 = DFMA, 5 = Fq Montgomery mul on the FP64 pipe (experiment),
+ * 6 = one integer and one FP64 product chain per thread, 7 = integer products in the even warps and FP64
+ * products in the odd warps of every CTA.  Returns operations (IMADs, or field muls) per
  * second sustained over all SMs -- the measured denominator of the integer roofline. */
 int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec);
 /* k_i * G for canonical scalars (fixed-base, used to make synthetic bases on the GPU):

@@ -6,6 +6,7 @@
 #include "../../zk-apps_b200/csrc/pairing.cuh"
 #include "../../zk-apps_b200/csrc/verify.cuh"
 #include "../../zk-apps_b200/csrc/glv.cuh"
+#include "../../zk-apps_b200/csrc/field_dfma.cuh"
 #include <vector>
 using namespace b200zk;
 
@@ -156,6 +157,17 @@ int hc_glv_phi(int group, const uint8_t* in, size_t n, uint8_t* out) {
             p.x = glv_phi_x(p.x);
             memcpy(out + i * 192, &p, 192);
         }
+    }
+    return 0;
+}
+// experiment: the Fq Montgomery product on double-precision FMAs (field_dfma.cuh); n pairs of 48 B Montgomery words
+int hc_fq_mul_dfma(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        Fq x, y;
+        memcpy(&x, a + i * 48, 48);
+        memcpy(&y, b + i * 48, 48);
+        const Fq r = dfma::fq_mul_dfma(x, y);
+        memcpy(out + i * 48, &r, 48);
     }
     return 0;
 }

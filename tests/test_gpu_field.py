@@ -77,3 +77,18 @@ def test_fixed_base_mul(ctx):
     assert g1 == [bls.G1.mul(bls.G1_GEN, k) for k in ks]
     g2 = util.g2_list(ctx.fixed_base_mul(2, sc[:32 * 10]))
     assert g2 == [bls.G2.mul(bls.G2_GEN, k) for k in ks[:10]]
+
+
+def test_fq_mul_on_the_fp64_pipe(ctx):
+    """Experiment (csrc/field_dfma.cuh): the Fq Montgomery product computed with DFMA on 48-bit limbs is bit-identical
+    to the integer-pipe product, on the device (op 7 = B200ZK_OP_MUL_DFMA)."""
+    import random
+    rnd = random.Random(21)
+    P = bls.P
+    vals = [rnd.randrange(P) for _ in range(4096)] + [0, 1, P - 1, P - 2, (1 << 380), (1 << 48) - 1, 1 << 48]
+    a = np.frombuffer(b"".join(bls.fq_to_mont_bytes(v) for v in vals), dtype=np.uint8).copy()
+    b = np.frombuffer(b"".join(bls.fq_to_mont_bytes(v) for v in vals[::-1]), dtype=np.uint8).copy()
+    ref = ctx.field_op(1, 2, a, b)
+    got = ctx.field_op(1, 7, a, b)
+    assert bytes(got) == bytes(ref)
+    assert bytes(got) == b"".join(bls.fq_to_mont_bytes(x * y % P) for x, y in zip(vals, vals[::-1]))

@@ -3,6 +3,7 @@
 // the device (2^24+ CPU scalar multiplications are infeasible).
 #include "common.cuh"
 #include "ec.cuh"
+#include "field_dfma.cuh"
 
 using namespace b200zk;
 
@@ -21,6 +22,10 @@ __global__ void field_op_kernel(int op, const F* a, const F* b, F* out, size_t n
         case B200ZK_OP_MUL: r = fp_mul(x, y); break;
         case B200ZK_OP_SQR: r = fp_sqr(x); break;
         case B200ZK_OP_INV: r = fp_inv(x); break;
+        case B200ZK_OP_MUL_DFMA:  // experiment: the same product on the FP64 pipe (Fq only)
+            if constexpr (sizeof(F) == sizeof(Fq)) r = dfma::fq_mul_dfma(x, y);
+            else r = fp_mul(x, y);
+            break;
         default: r = x; break;
     }
     out[i] = r;
@@ -123,6 +128,50 @@ __global__ void peak_fpmul(Fp<C>* out, const Fp<C>* in) {
     if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u) out[0] = a;
 }
 
+// Fq products on the FP64 pipe (field_dfma.cuh), same chain as peak_fpmul
+__global__ void peak_fqmul_dfma(Fq* out, const Fq* in) {
+    Fq a = in[0], b = in[1];
+    a.v[0] ^= threadIdx.x;
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        a = dfma::fq_mul_dfma(a, b);
+        b = dfma::fq_mul_dfma(b, a);
+    }
+    if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u) out[0] = a;
+}
+
+// two independent chains per thread, one on each pipe: what a kernel that splits its products between the
+// integer multiplier and the FP64 unit could sustain
+__global__ void peak_fqmul_both(Fq* out, const Fq* in) {
+    Fq a = in[0], b = in[1], c = in[1], d = in[0];
+    a.v[0] ^= threadIdx.x;
+    c.v[0] ^= threadIdx.x;
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        a = fp_mul(a, b);
+        c = dfma::fq_mul_dfma(c, d);
+        b = fp_mul(b, a);
+        d = dfma::fq_mul_dfma(d, c);
+    }
+    if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u && c.v[2] == 1u && d.v[3] == 2u) out[0] = a;
+}
+
+// warp-specialised: even warps keep the integer multiplier busy, odd warps the FP64 unit (2 CTAs/SM = 8 + 8 warps)
+__global__ void __launch_bounds__(256, 2) peak_fqmul_split(Fq* out, const Fq* in) {
+    Fq a = in[0], b = in[1];
+    a.v[0] ^= threadIdx.x;
+    if ((threadIdx.x >> 5) & 1) {
+        for (int it = 0; it < PEAK_ITERS / 2; it++) {
+            a = dfma::fq_mul_dfma(a, b);
+            b = dfma::fq_mul_dfma(b, a);
+        }
+    } else {
+        for (int it = 0; it < PEAK_ITERS / 2; it++) {
+            a = fp_mul(a, b);
+            b = fp_mul(b, a);
+        }
+    }
+    if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u) out[0] = a;
+}
+
 // ---------------------------------------------------------------- fixed-base multiplication
 template <class F>
 __global__ void fixed_base_kernel(const Affine<F>* gen, const uint32_t* scalars, size_t n, Affine<F>* out) {
@@ -195,7 +244,7 @@ int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, co
     if (n == 0) return B200ZK_OK;
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     bool conv = op == B200ZK_OP_TO_MONT || op == B200ZK_OP_FROM_MONT;
-    bool binary = op == B200ZK_OP_ADD || op == B200ZK_OP_SUB || op == B200ZK_OP_MUL;
+    bool binary = op == B200ZK_OP_ADD || op == B200ZK_OP_SUB || op == B200ZK_OP_MUL || op == B200ZK_OP_MUL_DFMA;
     if (binary && !b) return fail(ctx, B200ZK_ERR_BAD_ARG, "binary op needs b");
     if (!binary) b = nullptr;
     switch (field) {
@@ -220,7 +269,8 @@ int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {
     twor[0] = Fr::one();
     twor[1] = fp_add(Fr::one(), Fr::one());
     if (kind == 2) B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, twor, sizeof(twor), cudaMemcpyHostToDevice, ctx->stream));
-    if (kind == 3) B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, two, sizeof(two), cudaMemcpyHostToDevice, ctx->stream));
+    if (kind == 3 || kind == 5 || kind == 6 || kind == 7)
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, two, sizeof(two), cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
     const int blocks = ctx->sm_count * 8;
     cudaEvent_t e0, e1;
@@ -250,6 +300,18 @@ int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {
             case 4:
                 peak_dfma<<<blocks, threads, 0, ctx->stream>>>((double*)dbuf + 256, 1.0000001, 1e-9);
                 ops = 8.0 * PEAK_ITERS;
+                break;
+            case 5:
+                peak_fqmul_dfma<<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = PEAK_ITERS;
+                break;
+            case 6:
+                peak_fqmul_both<<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = 2.0 * PEAK_ITERS;
+                break;
+            case 7:
+                peak_fqmul_split<<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = PEAK_ITERS;
                 break;
             default: return fail(ctx, B200ZK_ERR_BAD_ARG, "unknown kind");
         }
