@@ -106,6 +106,11 @@ int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, co
  * products in the odd warps of every CTA.  Returns operations (IMADs, or field muls) per
  * second sustained over all SMs -- the measured denominator of the integer roofline. */
 int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec);
+/* Groundwork (csrc/ec_batch_affine.cuh): out[i] = p[i] + q[i] for n pairs of affine points (host buffers, FFI
+ * layout), one thread per `chunk` (1..64) consecutive pairs sharing one inversion.  ms_batch / ms_xyzz (may be
+ * NULL): best-of-3 device time of that kernel and of the same additions done as XYZZ mixed additions. */
+int b200zk_dbg_batch_add_affine(b200zk_ctx* ctx, int group, const uint8_t* p, const uint8_t* q, size_t n, int chunk,
+                                uint8_t* out, double* ms_batch, double* ms_xyzz);
 /* k_i * G for canonical scalars (fixed-base, used to make synthetic bases on the GPU):
  * group 1 -> 96 B G1 affine each, group 2 -> 192 B G2 affine each; host buffers. */
 int b200zk_fixed_base_mul(b200zk_ctx* ctx, int group, const uint8_t* scalars, size_t n, uint8_t* out_points);

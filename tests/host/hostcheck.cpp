@@ -7,7 +7,9 @@
 #include "../../zk-apps_b200/csrc/verify.cuh"
 #include "../../zk-apps_b200/csrc/glv.cuh"
 #include "../../zk-apps_b200/csrc/field_dfma.cuh"
+#include "../../zk-apps_b200/csrc/ec_batch_affine.cuh"
 #include <vector>
+#include <algorithm>
 using namespace b200zk;
 
 template <class F> static void field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
@@ -54,6 +56,62 @@ template <class F> static void madd_chain(const uint8_t* pts, const uint8_t* neg
     Affine<F> r = ec_to_affine(acc);
     memcpy(out, &r, sizeof(r));
 }
+// groundwork for the batched-affine bucket accumulation (ec_batch_affine.cuh): per-bucket sums by rounds of pairwise
+// additions inside each bucket, every round one flat array of pairs cut into chunks of `chunk` pairs with one inversion
+// each -- the schedule a GPU kernel would run (thread = chunk)
+template <class F>
+static void bucket_sums_batch_affine(const uint8_t* points, size_t n, const uint32_t* ids, uint32_t n_buckets, int chunk,
+                                     uint8_t* out) {
+    std::vector<Affine<F>> cur(n);
+    if (n) memcpy(cur.data(), points, n * sizeof(Affine<F>));
+    std::vector<size_t> off(n_buckets + 1, 0);
+    for (size_t i = 0; i < n; i++) off[ids[i] + 1]++;
+    for (uint32_t b = 0; b < n_buckets; b++) off[b + 1] += off[b];
+    for (;;) {
+        bool more = false;
+        std::vector<size_t> noff(n_buckets + 1, 0);
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            const size_t sz = off[b + 1] - off[b];
+            noff[b + 1] = noff[b] + (sz + 1) / 2;
+            if (sz > 1) more = true;
+        }
+        if (!more) break;
+        const size_t total = noff[n_buckets];
+        std::vector<Affine<F>> P(total), Q(total), R(total);
+        for (uint32_t b = 0; b < n_buckets; b++) {
+            const size_t sz = off[b + 1] - off[b];
+            for (size_t i = 0; i < (sz + 1) / 2; i++) {
+                P[noff[b] + i] = cur[off[b] + 2 * i];
+                Q[noff[b] + i] = 2 * i + 1 < sz ? cur[off[b] + 2 * i + 1] : Affine<F>::inf();  // odd one out: P + inf
+            }
+        }
+        std::vector<F> pre((size_t)chunk);
+        for (size_t c = 0; c < total; c += (size_t)chunk) {
+            const int m = (int)std::min((size_t)chunk, total - c);
+            ec_batch_add_affine(P.data() + c, Q.data() + c, R.data() + c, m, pre.data());
+        }
+        cur.swap(R);
+        off.swap(noff);
+    }
+    for (uint32_t b = 0; b < n_buckets; b++) {
+        const Affine<F> r = off[b + 1] > off[b] ? cur[off[b]] : Affine<F>::inf();
+        memcpy(out + (size_t)b * sizeof(Affine<F>), &r, sizeof(Affine<F>));
+    }
+}
+
+template <class F>
+static void batch_add_affine(const uint8_t* p, const uint8_t* q, size_t n, int chunk, uint8_t* out) {
+    std::vector<Affine<F>> P(n), Q(n), R(n);
+    memcpy(P.data(), p, n * sizeof(Affine<F>));
+    memcpy(Q.data(), q, n * sizeof(Affine<F>));
+    std::vector<F> pre((size_t)chunk);
+    for (size_t c = 0; c < n; c += (size_t)chunk) {
+        const int m = (int)std::min((size_t)chunk, n - c);
+        ec_batch_add_affine(P.data() + c, Q.data() + c, R.data() + c, m, pre.data());
+    }
+    memcpy(out, R.data(), n * sizeof(Affine<F>));
+}
+
 extern "C" {
 int hc_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
     if (op == 5 || op == 6) { if (field == 0) conv<FrCfg>(op, a, out, n); else conv<FqCfg>(op, a, out, n); return 0; }
@@ -169,6 +227,17 @@ int hc_fq_mul_dfma(const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
         const Fq r = dfma::fq_mul_dfma(x, y);
         memcpy(out + i * 48, &r, 48);
     }
+    return 0;
+}
+int hc_batch_add_affine(int group, const uint8_t* p, const uint8_t* q, size_t n, int chunk, uint8_t* out) {
+    if (group == 1) batch_add_affine<Fq>(p, q, n, chunk, out); else batch_add_affine<Fq2>(p, q, n, chunk, out);
+    return 0;
+}
+// ids: bucket of every point, ascending
+int hc_bucket_sums_batch_affine(int group, const uint8_t* points, size_t n, const uint32_t* ids, uint32_t n_buckets,
+                                int chunk, uint8_t* out) {
+    if (group == 1) bucket_sums_batch_affine<Fq>(points, n, ids, n_buckets, chunk, out);
+    else bucket_sums_batch_affine<Fq2>(points, n, ids, n_buckets, chunk, out);
     return 0;
 }
 }

@@ -92,3 +92,18 @@ def test_fq_mul_on_the_fp64_pipe(ctx):
     got = ctx.field_op(1, 7, a, b)
     assert bytes(got) == bytes(ref)
     assert bytes(got) == b"".join(bls.fq_to_mont_bytes(x * y % P) for x, y in zip(vals, vals[::-1]))
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_batch_affine_addition_kernel(ctx, group):
+    """Groundwork (csrc/ec_batch_affine.cuh): chunks of affine additions sharing one inversion on the device, with the
+    special cases inside a chunk, against the oracle."""
+    cv, enc, dec = (bls.G1, util.g1_array, util.g1_list) if group == 1 else (bls.G2, util.g2_array, util.g2_list)
+    rnd = random.Random(50 + group)
+    pts = [cv.mul(cv.gen, rnd.randrange(1, 1 << 40)) for _ in range(40)]
+    P = pts[:20] + [None, pts[0], None, pts[3], pts[4], pts[5]]
+    Q = pts[20:] + [pts[1], None, None, pts[3], cv.neg(pts[4]), pts[6]]
+    want = [cv.add(a, b) for a, b in zip(P, Q)]
+    for chunk in (1, 3, 32, 64):
+        out, _, _ = ctx.batch_add_affine(group, enc(P), enc(Q), chunk)
+        assert dec(out) == want, chunk

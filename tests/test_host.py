@@ -36,6 +36,8 @@ def hc(built):
     L.hc_glv_split.argtypes = [vp, C.c_size_t, vp, vp]
     L.hc_glv_phi.argtypes = [C.c_int, vp, C.c_size_t, vp]
     L.hc_fq_mul_dfma.argtypes = [vp, vp, vp, C.c_size_t]
+    L.hc_batch_add_affine.argtypes = [C.c_int, vp, vp, C.c_size_t, C.c_int, vp]
+    L.hc_bucket_sums_batch_affine.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_uint32, C.c_int, vp]
     return L
 
 
@@ -261,3 +263,37 @@ def test_fq_mul_dfma(hc):
     hc.hc_fq_mul_dfma(_p(raw), _p(raw[::1].copy()), _p(out2), 4)
     hc.hc_field_op(1, 2, _p(raw), _p(raw), _p(ref2), 4)
     assert bytes(out2) == bytes(ref2)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_batch_affine_addition(hc, group):
+    """ec_batch_affine.cuh (groundwork): chunks of affine additions sharing one inversion, with every special case inside
+    a chunk (infinite operands, P + P, P + (-P)), and the round-by-round bucket sums built on it, against the oracle."""
+    cv, enc, dec = (bls.G1, util.g1_array, util.g1_list) if group == 1 else (bls.G2, util.g2_array, util.g2_list)
+    rnd = random.Random(40 + group)
+    pts = [cv.mul(cv.gen, rnd.randrange(1, 1 << 40)) for _ in range(24)]
+    neg = lambda p: cv.neg(p) if p is not None else None
+    P = pts[:12] + [None, pts[0], None, pts[3], pts[4], pts[5]]
+    Q = pts[12:] + [pts[1], None, None, pts[3], neg(pts[4]), pts[6]]
+    want = [cv.add(a, b) for a, b in zip(P, Q)]
+    for chunk in (1, 2, 5, 32):
+        out = np.zeros(len(P) * (96 if group == 1 else 192), dtype=np.uint8)
+        hc.hc_batch_add_affine(group, _p(enc(P)), _p(enc(Q)), len(P), chunk, _p(out))
+        assert dec(out) == want, chunk
+    # bucket sums: 7 buckets (one empty, one singleton), duplicates and opposite points inside a bucket
+    members = {0: pts[:9], 1: [pts[9]], 3: [pts[10], pts[10], pts[11]], 4: [pts[12], neg(pts[12])],
+               5: [pts[13], neg(pts[13]), pts[14]], 6: pts[15:] + [None, pts[15]]}
+    flat, ids = [], []
+    for b in sorted(members):
+        flat += members[b]
+        ids += [b] * len(members[b])
+    want = []
+    for b in range(7):
+        acc = None
+        for p in members.get(b, []):
+            acc = cv.add(acc, p)
+        want.append(acc)
+    for chunk in (1, 3, 16):
+        out = np.zeros(7 * (96 if group == 1 else 192), dtype=np.uint8)
+        hc.hc_bucket_sums_batch_affine(group, _p(enc(flat)), len(flat), _p(np.array(ids, dtype=np.uint32)), 7, chunk, _p(out))
+        assert dec(out) == want, chunk

@@ -57,7 +57,7 @@ def build_cuda(verbose: bool = False) -> str:
 def build_hostcheck() -> str:
     src = os.path.join(ROOT, "tests", "host", "hostcheck.cpp")
     out = os.path.join(ROOT, "tests", "host", "libhostcheck.so")
-    deps = [src] + [os.path.join(CSRC, f) for f in ("field.cuh", "ec.cuh", "pairing.cuh", "pairing_consts.cuh", "verify.cuh", "glv.cuh", "field_dfma.cuh")]
+    deps = [src] + [os.path.join(CSRC, f) for f in ("field.cuh", "ec.cuh", "pairing.cuh", "pairing_consts.cuh", "verify.cuh", "glv.cuh", "field_dfma.cuh", "ec_batch_affine.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < _newest(deps):
         _run(["g++", "-O2", "-std=c++17", "-frounding-math", "-shared", "-fPIC", "-x", "c++", src, "-o", out])  # field_dfma.cuh sets the rounding mode
     return out

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "ec.cuh"
 #include "field_dfma.cuh"
+#include "ec_batch_affine.cuh"
 
 using namespace b200zk;
 
@@ -172,6 +173,74 @@ __global__ void __launch_bounds__(256, 2) peak_fqmul_split(Fq* out, const Fq* in
     if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u) out[0] = a;
 }
 
+// ---------------------------------------------------------------- batched affine addition (groundwork)
+// thread t adds the pairs [t * chunk, (t + 1) * chunk) with one inversion; pre[] lives in local memory
+constexpr int BA_MAX_CHUNK = 64;
+template <class F>
+__global__ void __launch_bounds__(128) batch_add_affine_kernel(const Affine<F>* __restrict__ p, const Affine<F>* __restrict__ q,
+                                                               size_t n, int chunk, Affine<F>* __restrict__ out) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t lo = t * (size_t)chunk;
+    if (lo >= n) return;
+    const int m = (int)(n - lo < (size_t)chunk ? n - lo : (size_t)chunk);
+    F pre[BA_MAX_CHUNK];
+    ec_batch_add_affine(p + lo, q + lo, out + lo, m, pre);
+}
+
+// the same additions the way the bucket accumulation does them today: XYZZ accumulator += affine, then to affine
+// is NOT included (the accumulation never leaves XYZZ); one mixed addition per pair, result discarded into a sum
+template <class F>
+__global__ void __launch_bounds__(128) xyzz_madd_kernel(const Affine<F>* __restrict__ p, const Affine<F>* __restrict__ q,
+                                                        size_t n, int chunk, XYZZ<F>* __restrict__ out) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t lo = t * (size_t)chunk;
+    if (lo >= n) return;
+    const int m = (int)(n - lo < (size_t)chunk ? n - lo : (size_t)chunk);
+    XYZZ<F> acc = XYZZ<F>::from_affine(p[lo]);
+    for (int i = 0; i < m; i++) ec_madd(acc, q[lo + i]);
+    out[t] = acc;
+}
+
+template <class F>
+int run_batch_add(b200zk_ctx* ctx, const uint8_t* p, const uint8_t* q, size_t n, int chunk, uint8_t* out, double* ms_batch,
+                  double* ms_xyzz) {
+    const size_t bytes = n * sizeof(Affine<F>);
+    void *dp, *dq, *dout, *dx;
+    B200ZK_TRY(scratch(ctx, "dbg_a", bytes, &dp));
+    B200ZK_TRY(scratch(ctx, "dbg_b", bytes, &dq));
+    B200ZK_TRY(scratch(ctx, "dbg_o", bytes, &dout));
+    const size_t threads = div_up(n, (size_t)chunk);
+    B200ZK_TRY(scratch(ctx, "dbg_x", threads * sizeof(XYZZ<F>), &dx));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dp, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(dq, q, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e[3];
+    for (auto& ev : e) B200ZK_CUDA(ctx, cudaEventCreate(&ev));
+    float best_b = 1e30f, best_x = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        B200ZK_CUDA(ctx, cudaEventRecord(e[0], ctx->stream));
+        batch_add_affine_kernel<F><<<div_up(threads, 128), 128, 0, ctx->stream>>>((const Affine<F>*)dp, (const Affine<F>*)dq, n,
+                                                                                 chunk, (Affine<F>*)dout);
+        B200ZK_TRY(check_launch(ctx, "batch_add_affine_kernel"));
+        B200ZK_CUDA(ctx, cudaEventRecord(e[1], ctx->stream));
+        xyzz_madd_kernel<F><<<div_up(threads, 128), 128, 0, ctx->stream>>>((const Affine<F>*)dp, (const Affine<F>*)dq, n, chunk,
+                                                                          (XYZZ<F>*)dx);
+        B200ZK_TRY(check_launch(ctx, "xyzz_madd_kernel"));
+        B200ZK_CUDA(ctx, cudaEventRecord(e[2], ctx->stream));
+        B200ZK_CUDA(ctx, cudaEventSynchronize(e[2]));
+        float a = 0, b = 0;
+        B200ZK_CUDA(ctx, cudaEventElapsedTime(&a, e[0], e[1]));
+        B200ZK_CUDA(ctx, cudaEventElapsedTime(&b, e[1], e[2]));
+        best_b = a < best_b ? a : best_b;
+        best_x = b < best_x ? b : best_x;
+    }
+    for (auto& ev : e) cudaEventDestroy(ev);
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ms_batch) *ms_batch = best_b;
+    if (ms_xyzz) *ms_xyzz = best_x;
+    return B200ZK_OK;
+}
+
 // ---------------------------------------------------------------- fixed-base multiplication
 template <class F>
 __global__ void fixed_base_kernel(const Affine<F>* gen, const uint32_t* scalars, size_t n, Affine<F>* out) {
@@ -255,6 +324,17 @@ int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, co
             return run_field_op<Fq2>(ctx, op, a, b, out, n);
         default: return fail(ctx, B200ZK_ERR_BAD_ARG, "unknown field");
     }
+}
+
+int b200zk_dbg_batch_add_affine(b200zk_ctx* ctx, int group, const uint8_t* p, const uint8_t* q, size_t n, int chunk,
+                                uint8_t* out, double* ms_batch, double* ms_xyzz) {
+    if (!ctx || !p || !q || !out) return B200ZK_ERR_BAD_ARG;
+    if (chunk < 1 || chunk > BA_MAX_CHUNK) return fail(ctx, B200ZK_ERR_BAD_ARG, "chunk must be 1..64");
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (group == 1) return run_batch_add<Fq>(ctx, p, q, n, chunk, out, ms_batch, ms_xyzz);
+    if (group == 2) return run_batch_add<Fq2>(ctx, p, q, n, chunk, out, ms_batch, ms_xyzz);
+    return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
 }
 
 int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {

@@ -64,6 +64,8 @@ def lib() -> C.CDLL:
             "b200zk_launch_count": (C.c_long, [vp]),
             "b200zk_dbg_field_op": (i32, [vp, i32, i32, vp, vp, vp, sz]),
             "b200zk_dbg_int_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
+            "b200zk_dbg_batch_add_affine": (i32, [vp, i32, vp, vp, C.c_size_t, i32, vp, C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double)]),
             "b200zk_fixed_base_mul": (i32, [vp, i32, vp, sz, vp]),
             "b200zk_fixed_base_mul_device": (i32, [vp, i32, vp, sz, vp]),
             "b200zk_ntt_fr": (i32, [vp, vp, u32, i32, vp, sz]),
@@ -251,6 +253,18 @@ class Context:
         v = C.c_double()
         self.check(lib().b200zk_dbg_int_peak(self._h, kind, C.byref(v)))
         return v.value
+
+    def batch_add_affine(self, group: int, p, q, chunk: int = 32):
+        """Groundwork kernel (csrc/ec_batch_affine.cuh): p[i] + q[i], `chunk` pairs per thread sharing one inversion.
+        -> (affine sums, ms of that kernel, ms of the same additions as XYZZ mixed additions)."""
+        pp, kp = _buf(p)
+        pq, kq = _buf(q)
+        n = kp.nbytes // (G1_BYTES if group == 1 else G2_BYTES)
+        out = np.empty(kp.nbytes, dtype=np.uint8)
+        a, b = C.c_double(), C.c_double()
+        self.check(lib().b200zk_dbg_batch_add_affine(self._h, group, pp, pq, n, chunk, out.ctypes.data_as(C.c_void_p),
+                                                     C.byref(a), C.byref(b)))
+        return out, a.value, b.value
 
     def fixed_base_mul(self, group: int, scalars) -> np.ndarray:
         ps, ks = _buf(scalars)
