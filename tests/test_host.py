@@ -298,3 +298,14 @@ def test_batch_affine_addition(hc, group):
         out = np.zeros(7 * (96 if group == 1 else 192), dtype=np.uint8)
         hc.hc_bucket_sums_batch_affine(group, _p(enc(flat)), len(flat), _p(np.array(ids, dtype=np.uint32)), 7, chunk, _p(out))
         assert dec(out) == want, chunk
+
+
+def test_tools_and_bench_parse():
+    """Every measurement script (bench.py, tools/*.py) at least compiles: they only run on a GPU box."""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
+    assert len(files) >= 10
+    for f in files:
+        py_compile.compile(f, doraise=True, cfile=os.devnull if os.name != "nt" else None)
