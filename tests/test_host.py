@@ -303,9 +303,8 @@ def test_batch_affine_addition(hc, group):
 def test_tools_and_bench_parse():
     """Every measurement script (bench.py, tools/*.py) at least compiles: they only run on a GPU box."""
     import glob
-    import py_compile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "tools", "*.py")))
     assert len(files) >= 10
     for f in files:
-        py_compile.compile(f, doraise=True, cfile=os.devnull if os.name != "nt" else None)
+        compile(open(f).read(), f, "exec")
