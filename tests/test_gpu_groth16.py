@@ -56,6 +56,20 @@ def test_unsatisfied_witness_is_reported(ctx):
     assert rc == -6                                                                       # B200ZK_ERR_UNSATISFIED
 
 
+def test_non_canonical_input_rows_are_unsatisfied_not_a_hang(ctx):
+    """input rows are caller-supplied words; one holding the unreduced word r (or anything >= r) used to reach
+    fp_inv and spin.  Such an instance must come back as `unsatisfied`, the other instances of the batch unaffected."""
+    relation = z.UpdateNoteRelation(rel.WITHDRAW, rel.TREE_HEIGHT)
+    good = rel.witness_to_inputs(rel.make_witness(5, rel.WITHDRAW))
+    arr = util.fr_mont_array(good * 4).copy().reshape(4, len(good), 32)
+    r_word = np.frombuffer(R.to_bytes(32, "little"), dtype=np.uint8)
+    arr[1, 13] = r_word                                   # path_shape[0] = the word r  (fed to fp_inv before the fix)
+    arr[2, 14 + 2 * rel.TREE_HEIGHT] = r_word             # old_account.token0 = r      (token difference inversion)
+    arr[3, 0] = 0xFF                                      # amount = 2^256 - 1
+    out, status = relation.witness_batch(ctx, arr.reshape(-1), 4)
+    assert list(status) == [0, 1, 1, 1]
+
+
 @pytest.fixture(scope="module")
 def withdraw_key(ctx):
     relation = z.UpdateNoteRelation(rel.WITHDRAW, rel.TREE_HEIGHT)

@@ -156,6 +156,24 @@ def test_host_field_ops(hc, field):
         assert bytes(out) == bytes(enc([fn(x, y) for x, y in zip(A, B)])), (field, op)
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_host_inversion_is_total_on_unreduced_words(hc, field):
+    """fp_inv used to spin forever on the raw word p (u becomes 0 after one subtraction).  Every N-limb
+    word is now reduced first: multiples of p give 0, anything else the inverse of its residue."""
+    mod, size = (R, 32) if field == 0 else (P, 48)
+    Rm = 1 << (8 * size)
+    words = [mod, 2 * mod if 2 * mod < Rm else mod, mod + 5, Rm - 1, mod + (mod - 1)]
+    raw = np.frombuffer(b"".join(w.to_bytes(size, "little") for w in words), dtype=np.uint8).copy()
+    out = np.zeros_like(raw)
+    hc.hc_field_op(field, 4, _p(raw), _p(raw), _p(out), len(words))
+    # the word w stands for the Montgomery form of (w mod p) * R^-1; its inverse in Montgomery form is (w mod p)^-1 * R^2
+    for i, w in enumerate(words):
+        got = int.from_bytes(bytes(out[i * size:(i + 1) * size]), "little")
+        wm = w % mod
+        want = pow(wm, -1, mod) * Rm * Rm % mod if wm else 0
+        assert got == want, (field, i)
+
+
 def test_host_mont_conversion(hc):
     vals = [0, 1, 7, R - 1, 1 << 200]
     canon = np.frombuffer(b"".join(bls.int_to_le(v, 32) for v in vals), dtype=np.uint8).copy()

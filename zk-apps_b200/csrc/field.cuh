@@ -392,7 +392,6 @@ HD Fp<C> fp_inv_fermat(const Fp<C>& a) {
 template <class C>
 HD Fp<C> fp_inv(const Fp<C>& a) {
     constexpr int N = C::N;
-    if (a.is_zero()) return a;
     uint32_t u[N], v[N];
     Fp<C> x1 = Fp<C>::zero(), x2 = Fp<C>::zero();
     x1.v[0] = 1;
@@ -400,6 +399,28 @@ HD Fp<C> fp_inv(const Fp<C>& a) {
     for (int i = 0; i < N; i++) {
         u[i] = a.v[i];
         v[i] = C::mod(i);
+    }
+    // Total on every N-limb word: a caller-supplied, unreduced word (u >= p; u == p in particular) would make
+    // the halving loop below spin on u = 0, so reduce first (at most 2^(32N) / p < 10 subtractions) and map
+    // every multiple of p to 0 like a == 0.
+    for (;;) {
+        uint32_t t[N];
+        uint64_t br = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint64_t d = (uint64_t)u[i] - v[i] - br;
+            t[i] = (uint32_t)d;
+            br = (d >> 63) & 1;
+        }
+        if (br) break;  // u < p
+#pragma unroll
+        for (int i = 0; i < N; i++) u[i] = t[i];
+    }
+    {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= u[i];
+        if (o == 0) return Fp<C>::zero();
     }
     auto is_one = [](const uint32_t* w) {
         uint32_t o = w[0] ^ 1u;

@@ -283,7 +283,7 @@ __device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_
     else partials[s0 + (run - (offsets[key] >> log_tl))] = acc;
 }
 
-template <class F, int MIN_BLOCKS>
+template <class F, int MIN_BLOCKS, class O>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F>* __restrict__ bases,
                                                       const Affine<F>* __restrict__ bases2, uint32_t n_split,
                                                       const uint32_t* __restrict__ offsets,
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
     // registers) + current point (48) + a second point (48) do not fit in 255 registers next to the formula's
     // temporaries (ncu: 1.4 GB of local-memory spill traffic per launch), so the next point is only prefetched
     // into L1 and loaded after the addition.
-    constexpr bool PREFETCH_TO_REGS = sizeof(F) == sizeof(Fq);
+    constexpr bool PREFETCH_TO_REGS = sizeof(F) == sizeof(Fq) && MIN_BLOCKS <= 3;
     for (;;) {
         const uint32_t kn = k + 1;
         Affine<F> nxt;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(np) + off));
             }
         }
-        ec_madd(acc, cur, neg);
+        ec_madd<F, O>(acc, cur, neg);
         if (kn >= end) break;
         if (kn == bend) {  // next entry belongs to a later bucket
             flush_bucket(key, run, log_tl, acc, offsets, soff, buckets, partials);
@@ -674,8 +674,21 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2", st);
         // resident CTAs per SM (register cap 65536 / (128 * blocks)); tunable for experiments
         static const int occ_env = getenv("B200ZK_ACC_BLOCKS") ? atoi(getenv("B200ZK_ACC_BLOCKS")) : 0;
-        const int occ = occ_env ? occ_env : 2;  // measured: 3 gains 1.6 % alone but crowds out the concurrent tails
-        auto kern = occ >= 4 ? msm_accumulate<F, 4> : occ == 3 ? msm_accumulate<F, 3> : msm_accumulate<F, 2>;
+        static const int occ2_env = getenv("B200ZK_ACC_BLOCKS_G2") ? atoi(getenv("B200ZK_ACC_BLOCKS_G2")) : occ_env;
+        const int occ_sel = sizeof(F) == sizeof(Fq) ? occ_env : occ2_env;
+        // measured (profiles/r02_acc_sweep.log, 128-proof step): with the call-based products G1 gains 8 % from a
+        // third resident CTA (24.1 -> 22.35 ms, 0.82 -> 0.885 of the Fq-mul peak; a fourth adds 0.5 % and costs the
+        // concurrent tails), G2 is best at 2 CTAs (255 registers, 12.9 ms; 168 registers spill: 13.2 ms)
+        const int occ = occ_sel ? occ_sel : (sizeof(F) == sizeof(Fq) ? 3 : 2);
+        // how the field products are issued (ec.cuh): 0 = expanded in place, 1 = calls to one Fq product / square
+        // (operands by value, in registers), 2 = G2 only: Fq2 products as calls around the Fq calls
+        static const int var_env = getenv("B200ZK_ACC_VARIANT") ? atoi(getenv("B200ZK_ACC_VARIANT")) : 1;
+        static const int var2_env = getenv("B200ZK_ACC_VARIANT_G2") ? atoi(getenv("B200ZK_ACC_VARIANT_G2")) : var_env;
+        const int variant = sizeof(F) == sizeof(Fq) ? std::min(var_env, 1) : var2_env;
+        auto kern = msm_accumulate<F, 2, CallOps>;
+        if (variant == 0) kern = occ >= 3 ? msm_accumulate<F, 3, InlineOps> : msm_accumulate<F, 2, InlineOps>;
+        else if (variant == 2) kern = occ >= 3 ? msm_accumulate<F, 3, NestedCallOps> : msm_accumulate<F, 2, NestedCallOps>;
+        else kern = occ >= 4 ? msm_accumulate<F, 4, CallOps> : occ == 3 ? msm_accumulate<F, 3, CallOps> : msm_accumulate<F, 2, CallOps>;
         // CTA width (<= 128): narrower CTAs leave registers for latency-bound CTAs of other MSMs (experiments)
         static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
         const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;

@@ -117,6 +117,25 @@ __global__ void __launch_bounds__(64) update_note_witness_kernel(const Fr* __res
     const uint32_t O_END = O_NACC_HASH + 2 * T;
     const bool wr = lane == 0;  // the lane that writes scalar witnesses
     bool ok = true;
+    {   // Input rows come from the caller unchecked: a word >= r is not a field element (ark's Fr cannot hold one).
+        // Such an instance is reported as unsatisfied and nothing below (inversions included) ever sees it.
+        bool canon = true;
+        for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x) {
+            const Fr v = ld_fr(in + i);
+            bool lt = false;  // v < r, most significant limb first
+            for (int k = 7; k >= 0; k--) {
+                if (v.v[k] != FrCfg::mod(k)) {
+                    lt = v.v[k] < FrCfg::mod(k);
+                    break;
+                }
+            }
+            canon = canon && lt;
+        }
+        if (!__syncthreads_and(canon ? 1 : 0)) {
+            if (threadIdx.x == 0) status[proof] = 1u | (O_END == num_vars ? 0u : 2u);
+            return;
+        }
+    }
     if (warp == 0) {
         // ---- z[0] = 1, instance variables, loaded witnesses
         if (wr) {
