@@ -50,7 +50,8 @@ typedef enum {
     B200ZK_ERR_MERKLE_LIMIT_EXCEEDED = -8,    /* ShielderError::MerkleTreeLimitExceeded   (contract/merkle.rs:49-51) */
     B200ZK_ERR_MERKLE_PROOF_GEN_FAIL = -9,    /* ShielderError::MerkleTreeProofGenFail    (contract/merkle.rs:91-93) */
     B200ZK_ERR_MERKLE_NON_EXISTING_NODE = -10,/* ShielderError::MerkleTreeNonExistingNode (contract/merkle.rs:42-46) */
-    B200ZK_ERR_BAD_ENCODING = -11             /* serialized key: truncated / invalid point (ark SerializationError::InvalidData) */
+    B200ZK_ERR_BAD_ENCODING = -11,            /* serialized key: truncated / invalid point (ark SerializationError::InvalidData) */
+    B200ZK_ERR_NCCL = -12                     /* NCCL missing at run time, or a communicator / collective call failed */
 } b200zk_status;
 
 enum { B200ZK_FIELD_FR = 0, B200ZK_FIELD_FQ = 1, B200ZK_FIELD_FQ2 = 2 };
@@ -58,8 +59,13 @@ enum { B200ZK_OP_ADD = 0, B200ZK_OP_SUB = 1, B200ZK_OP_MUL = 2, B200ZK_OP_SQR = 
        B200ZK_OP_TO_MONT = 5, B200ZK_OP_FROM_MONT = 6,
        B200ZK_OP_MUL_DFMA = 7 /* experiment: Fq product on the FP64 pipe (csrc/field_dfma.cuh); Fq only */ };
 
-/* ---- context ------------------------------------------------------------------------- */
+/* ---- context -------------------------------------------------------------------------
+ * One ctx per GPU.  The deployment model is one host thread (or process) per GPU, each with its own ctx
+ * (b200zk_init(device)); GPUs cooperate through a communicator attached to the ctx (b200zk_comm_init below).
+ * b200zk_init_multi is the single-process form SURVEY.md section 8b sketched as `b200zk_init(n_gpus)`: it creates
+ * the contexts of devices 0..n_gpus-1 and one NCCL communicator over them (ncclCommInitAll). */
 int b200zk_init(int device, b200zk_ctx** out);
+int b200zk_init_multi(int n_gpus, b200zk_ctx** out /* n_gpus entries */);
 void b200zk_destroy(b200zk_ctx* ctx);
 const char* b200zk_last_error(b200zk_ctx* ctx);
 int b200zk_sync(b200zk_ctx* ctx);
@@ -68,7 +74,11 @@ int b200zk_sync(b200zk_ctx* ctx);
  * "msm_parts" (default 0 = automatic: 4 from 2^23 points, else 1): number of window groups a single
  * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream.
  * "msm_glv" (default 1): MSMs (G1 and G2) over plain bases split every scalar as k1 + k2*lambda (two non-negative
- * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way. */
+ * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way FOR BASES
+ * IN THE ORDER-r SUBGROUP (k*P = k1*P + k2*phi(P) needs phi(P) = lambda*P, which holds on G1/G2 only: for the
+ * order-3 point (0, 2) the two paths differ).  Every proving-key query and every ark `G1Affine`/`G2Affine` that
+ * went through checked deserialisation is in the subgroup; for bases of unknown origin call
+ * b200zk_points_validate(check_subgroup = 1) first or set msm_glv = 0. */
 int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value);
 /* raw device memory for callers that keep operands resident in HBM */
 int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** dptr);
@@ -149,7 +159,10 @@ int b200zk_copy2d_device(b200zk_ctx* ctx, void* d_dst, size_t dpitch, const void
  * [recall]; absent from the reference, rows a7/a8).  sum_i scalars[i] * bases[i], result affine.
  * inf_flags: n bytes (non-zero = base is the point at infinity) or NULL.
  * b200zk_msm_* take host buffers; *_resident take bases uploaded once (optionally with the
- * per-window multiples 2^(c*w) * P precomputed, which removes the window combine). */
+ * per-window multiples 2^(c*w) * P precomputed, which removes the window combine).
+ * PRECONDITIONS (not checked on this path, as in ark's msm_bigint): scalars are canonical, i.e. < r -- what
+ * `Fr::into_bigint()` yields; a 256-bit word >= 2^255 can lose the carry out of the top signed window -- and the
+ * bases are reduced affine points of the order-r subgroup (see "msm_glv" above; b200zk_points_validate checks). */
 int b200zk_msm_g1(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags,
                   const uint8_t* scalars, size_t n, uint8_t out_affine[96], uint8_t* out_is_inf);
 int b200zk_msm_g2(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flags,
@@ -167,11 +180,42 @@ int b200zk_msm_resident(b200zk_ctx* ctx, const b200zk_bases* h, const void* scal
                         int scalars_on_device, size_t n, size_t batch, uint8_t* out_affine,
                         uint8_t* out_is_inf);
 
-/* ---- multi-GPU building blocks: a large MSM is split by point range, one
- * rank per GPU; every rank computes the MSM of its slice with b200zk_msm_resident_device, which leaves
- * the affine partial in device memory (e.g. directly in this rank's slot of an NCCL all_gather
- * buffer) and does NOT synchronise the host; after the all_gather b200zk_points_sum[_device] adds the
- * n partials (curve addition is not an NCCL reduction op).  zk-apps_b200/sharded.py is the host side. */
+/* ---- multi-GPU (csrc/comm.cu) ---------------------------------------------------
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", or the path in $B200ZK_NCCL_LIB): the library has no link-time
+ * dependency on it, and without it only the entry points of this section fail (B200ZK_ERR_NCCL).
+ *   b200zk_comm_unique_id: rank 0 obtains the 128-byte ncclUniqueId; the host distributes it to the other ranks by
+ *     its own means (a file, MPI, torch.distributed ...).
+ *   b200zk_comm_init(ctx, id, rank, world): collective over all ranks (ncclCommInitRank); world == 1 needs no id
+ *     and no NCCL.  b200zk_comm_destroy releases it (b200zk_destroy does so too).
+ *   b200zk_msm_sharded[_device]: VariableBaseMSM over world GPUs, split by contiguous point range: h_local /
+ *     scalars_local / n_local are THIS rank's slice (any sizes, 0 allowed).  Local bucket pipeline -> the affine
+ *     partial is written by the last kernel straight into this rank's slot of the all_gather buffer -> in-place
+ *     ncclAllGather of world * 96 B (G1) / 192 B (G2) on the ctx stream -> every rank adds the partials (curve
+ *     addition is not an NCCL reduction op).  Every rank gets the same affine result.  The _device form leaves it
+ *     in device memory and does not synchronise the host: kernels, collective and sum are one stream of work.
+ *   b200zk_msm_sharded_multi: the same for the contexts of b200zk_init_multi, driven by ONE host thread (the
+ *     collectives of all ranks are issued inside one NCCL group).
+ *   b200zk_ntt_sharded_device: radix-2 Fr NTT of size 2^log_n = n1 * n2 (n1 = 2^log_n1) as a four-step transform
+ *     with ONE exchange.  Layout L(a, b) of a length-a*b vector v over G ranks: rank g holds
+ *     local[c][j] = v[j*b + g*(b/G) + c], c < b/G, j < a.  Input: this rank's part in L(n1, n2), n/G elements,
+ *     transformed in place; output: the transform in L(n2, n1) -- so the opposite direction with log_n1' = log_n -
+ *     log_n1 consumes it directly and returns to L(n1, n2).  G must be a power of two <= min(n1, n2).  Asynchronous
+ *     on the ctx stream.  NTTs up to 2^22 are faster on one GPU: replicas only.
+ * The building blocks stay public: b200zk_msm_resident_device (partial left in device memory, no host sync) and
+ * b200zk_points_sum[_device]. */
+#define B200ZK_COMM_ID_BYTES 128
+int b200zk_comm_unique_id(uint8_t id_out[128]);
+int b200zk_comm_init(b200zk_ctx* ctx, const uint8_t id[128], int rank, int world);
+int b200zk_comm_destroy(b200zk_ctx* ctx);
+int b200zk_comm_info(const b200zk_ctx* ctx, int* rank, int* world);
+int b200zk_msm_sharded(b200zk_ctx* ctx, const b200zk_bases* h_local, const void* scalars_local, int scalars_on_device,
+                       size_t n_local, uint8_t* out_affine, uint8_t* out_is_inf);
+int b200zk_msm_sharded_device(b200zk_ctx* ctx, const b200zk_bases* h_local, const void* scalars_local,
+                              int scalars_on_device, size_t n_local, void* d_out_affine);
+int b200zk_msm_sharded_multi(b200zk_ctx** ctxs, int n_gpus, const b200zk_bases** h_local,
+                             const void** scalars_local, int scalars_on_device, const size_t* n_local,
+                             uint8_t* out_affine, uint8_t* out_is_inf);
+int b200zk_ntt_sharded_device(b200zk_ctx* ctx, void* d_local, uint32_t log_n, uint32_t log_n1, int inverse);
 int b200zk_msm_resident_device(b200zk_ctx* ctx, const b200zk_bases* h, const void* scalars, int scalars_on_device,
                                size_t n, size_t batch, void* d_out_affine);
 int b200zk_points_sum(b200zk_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out_affine,
@@ -186,6 +230,12 @@ int b200zk_points_sum_device(b200zk_ctx* ctx, int group, const void* d_points, s
  * witness...].  Matrices come out as CSR, coefficients 32 B Montgomery Fr. */
 typedef struct b200zk_r1cs b200zk_r1cs;
 int b200zk_update_note_r1cs(int kind, uint32_t tree_height, b200zk_r1cs** out);
+/* R1CS of update_account_circuit as a relation of its own (shielder/relations/src/relations/update_account.rs:68-95;
+ * UpdateAccountInput :18-30), same concrete Account/Operation.  z = [1, instance (old_account_hash,
+ * new_account_hash, amount, token, user -- the struct's "public inputs" in field order), witness (old_account:
+ * token0, balance0, token1, balance1, then the gadget witnesses)].  It is the sub-circuit update_note_circuit calls
+ * last (update_note.rs:141-148); both are built from one gadget so they cannot drift. */
+int b200zk_update_account_r1cs(int kind, b200zk_r1cs** out);
 void b200zk_r1cs_free(b200zk_r1cs* r);
 int b200zk_r1cs_shape(const b200zk_r1cs* r, uint64_t* num_constraints, uint64_t* num_inputs /* incl. ONE */,
                       uint64_t* num_aux, uint64_t nnz[3]);
@@ -209,6 +259,11 @@ int b200zk_poseidon_constants(uint8_t* round_constants, uint8_t* mds);
 int b200zk_poseidon_hash_batch(b200zk_ctx* ctx, const uint8_t* inputs, size_t n_hashes, uint32_t arity, uint8_t* out);
 int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
                                      uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status);
+/* same for the update-account relation: inputs = batch rows of 9 Fr in UpdateAccountInput::new argument order
+ * (update_account.rs:37-42): old_account_hash | new_account_hash | operation (amount, token, user) |
+ * old_account (token0, balance0, token1, balance1).  Any input word >= r marks the instance unsatisfied. */
+int b200zk_update_account_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
+                                        uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status);
 
 /* ---- the note tree (csrc/merkle.cu) -----------------------------------
  * Replaces the reference's MerkleTree<DEPTH> (shielder/contract/merkle.rs:11-106) with the circuit's hash:
@@ -269,6 +324,9 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
                                uint8_t* points_out);
 int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
                                    const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status);
+/* witness generation + proving for a key made from b200zk_update_account_r1cs (rows of 9 Fr, see above) */
+int b200zk_update_account_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
+                                      const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status);
 /* same with the instance inputs already resident in device memory (r, s, proofs stay host buffers) */
 int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,
                                           const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
@@ -290,7 +348,8 @@ int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, 
  * b200zk_groth16_verify_aggregate: ONE verdict for the whole batch from a random linear combination
  *   (prod e(r_i A_i, B_i) = e(alpha,beta)^(sum r_i) e(sum r_i L_i, gamma) e(sum r_i C_i, delta)): batch + 3
  *   Miller loops and one final exponentiation instead of 3 * batch and batch.  coeffs = batch * 16 B
- *   little-endian 128-bit randomisers chosen by the CALLER (soundness error 2^-128 over their choice).
+ *   little-endian 128-bit randomisers chosen by the CALLER (soundness error 2^-128 over their choice); always a
+ *   host buffer; a zero coefficient would exclude its proof from the check and is rejected (BAD_ARG).
  *   *all_valid = 1 iff every proof decodes and the combined equation holds.
  * b200zk_points_compress / _decompress: the zcash / ark-serialize compressed encoding (48 B G1, 96 B G2:
  *   big-endian x, flag bits 0x80 compressed, 0x40 infinity, 0x20 y lexicographically largest; G2 = x.c1|x.c0),
@@ -320,6 +379,10 @@ int b200zk_groth16_verify_aggregate(b200zk_ctx* ctx, const b200zk_vk* vk, const 
 int b200zk_points_compress(b200zk_ctx* ctx, int group, const uint8_t* affine, size_t n, uint8_t* out);
 int b200zk_points_decompress(b200zk_ctx* ctx, int group, const uint8_t* in, size_t n, int check_subgroup,
                              uint8_t* out_affine, int32_t* status);
+/* per-point status (same codes as _decompress) of n affine points in the FFI layout: every coordinate word < p,
+ * on the curve, and -- with check_subgroup -- in the order-r subgroup (the precondition of the GLV MSM path) */
+int b200zk_points_validate(b200zk_ctx* ctx, int group, const uint8_t* affine, size_t n, int check_subgroup,
+                           int32_t* status);
 int b200zk_vk_serialize(b200zk_ctx* ctx, const b200zk_vk* vk, uint8_t* out, size_t* len);
 int b200zk_vk_deserialize(b200zk_ctx* ctx, const uint8_t* in, size_t len, int check_subgroup, b200zk_vk** out);
 int b200zk_pk_serialize(b200zk_ctx* ctx, const b200zk_pk* pk, const b200zk_vk* vk, uint8_t* out, size_t* len);

@@ -7,9 +7,12 @@ Reference call sites (the only first-party facts): parameters T=5, RATE=4, R_F=8
 through `hash_fix_len_array` (update_note.rs:100,131; update_account.rs:62;
 merkle_proof.rs:56).
 
-PARITY UNPINNED: the permutation lives in the un-vendored halo2-base 0.4.1 @86376e7
-(shielder/Cargo.lock:414-416); no hash vector exists in the tree.  What is restated
-here ([recall]):
+PARITY UNPINNED against the reference: the permutation lives in the un-vendored halo2-base 0.4.1 @86376e7
+(shielder/Cargo.lock:414-416); no hash vector exists in the tree.  Third-party pin (round 2): the Grain
+generator and the round structure below, instantiated for the public BN254 instance x5_254_3, reproduce the
+published round constants, MDS matrix and the circomlib vector poseidon([1, 2]) (tests/test_oracle_kat.py) --
+so constants generation and permutation are not from recall any more; the sponge conventions of halo2-base
+(initial 2^64, padding, output lane) still are.  What is restated here ([recall]):
   * constants from the Poseidon reference Grain LFSR (field tag 1, S-box tag 0 = x^alpha,
     n = 255 bits, t, R_F, R_P), round constants with rejection sampling, Cauchy MDS from
     2t elements without rejection (first t = xs, next t = ys), SECURE_MDS = 0 -> the
@@ -84,22 +87,29 @@ def constants(t: int = T_WIDTH, r_f: int = R_F, r_p: int = R_P, modulus: int = R
     return rc, mds
 
 
-def permute(state, trace=None):
-    """Plain Poseidon permutation.  If `trace` is a list, appends (x^2, x^4, x^5) per S-box in
-    evaluation order -- exactly the R1CS witness block of one permutation."""
-    rc, mds = constants()
-    t = T_WIDTH
-    s = [x % R for x in state]
-    half = R_F // 2
-    for rnd in range(R_F + R_P):
-        s = [(s[i] + rc[rnd][i]) % R for i in range(t)]
-        full = rnd < half or rnd >= half + R_P
+def permute_params(state, t: int, r_f: int, r_p: int, modulus: int, bits: int, trace=None):
+    """Plain Poseidon permutation (x^5) for any instance the Grain generator can parameterise.  Used with the
+    shielder parameters below and -- as a third-party pin of generator AND round structure -- with the public
+    BN254 instance x5_254_3 (t=3, R_F=8, R_P=57), whose constants and test vector are widely published
+    (tests/test_oracle_kat.py::test_poseidon_generator_and_permutation_match_the_public_bn254_instance)."""
+    rc, mds = constants(t, r_f, r_p, modulus, bits)
+    s = [x % modulus for x in state]
+    half = r_f // 2
+    for rnd in range(r_f + r_p):
+        s = [(s[i] + rc[rnd][i]) % modulus for i in range(t)]
+        full = rnd < half or rnd >= half + r_p
         for i in range(t if full else 1):
-            x2 = s[i] * s[i] % R; x4 = x2 * x2 % R; x5 = x4 * s[i] % R
+            x2 = s[i] * s[i] % modulus; x4 = x2 * x2 % modulus; x5 = x4 * s[i] % modulus
             if trace is not None: trace.append((x2, x4, x5))
             s[i] = x5
-        s = [sum(mds[i][j] * s[j] for j in range(t)) % R for i in range(t)]
+        s = [sum(mds[i][j] * s[j] for j in range(t)) % modulus for i in range(t)]
     return s
+
+
+def permute(state, trace=None):
+    """The shielder instance (BLS12-381 Fr, T=5, R_F=8, R_P=56).  If `trace` is a list, appends (x^2, x^4, x^5) per
+    S-box in evaluation order -- exactly the R1CS witness block of one permutation."""
+    return permute_params(state, T_WIDTH, R_F, R_P, R, FIELD_BITS, trace)
 
 
 def hash_fix_len_array(inputs, trace=None) -> int:

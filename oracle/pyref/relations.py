@@ -171,6 +171,75 @@ def synthesize_update_note(w: UpdateNoteWitness, tree_height: int = TREE_HEIGHT)
     return cs
 
 
+# ------------------------------------------------------------------------ update-account as a relation of its own
+@dataclass
+class UpdateAccountWitness:
+    """UpdateAccountInput (relations/src/relations/update_account.rs:18-30): public old/new account hash and the
+    operation, witness = the old account."""
+    kind: int
+    old_account_hash: int
+    new_account_hash: int
+    amount: int
+    token: int
+    user: int
+    old_account: Account
+
+    def public_inputs(self):
+        return [self.old_account_hash % R, self.new_account_hash % R, self.amount % R, self.token % R, self.user % R]
+
+
+def make_account_witness(seed: int, kind: int = WITHDRAW) -> UpdateAccountWitness:
+    from .algos import SplitMix64
+    g = SplitMix64(0xACC00000 + seed)
+    tokens = [g.fr(), g.fr()]
+    balances = [(g.next() | (g.next() << 64)) % (1 << 126), g.next()]
+    old = Account(tokens, balances)
+    which = g.next() & 1
+    amount = (g.next() % (old.balances[which] + 1)) if kind == WITHDRAW else g.next()
+    new = old.update(kind, amount, tokens[which])
+    return UpdateAccountWitness(kind, old.hash(), new.hash(), amount, tokens[which], g.fr(), old)
+
+
+def _update_account_gadget(cs, kind, amount, token, acc_tokens, acc_balances, old_account_hash, new_account_hash):
+    """update_account_circuit (update_account.rs:68-95) over already allocated variables; shared by both relations."""
+    old_vec = []
+    for t, b in zip(acc_tokens, acc_balances): old_vec += [t, b]
+    assert_equal(cs, poseidon_hash(cs, old_vec), old_account_hash)  # :79-85
+    range_bits(cs, amount, BALANCE_BITS)                            # new_account = old_account.update(operation)  :87
+    matches = LC()
+    new_vec = []
+    for t, b in zip(acc_tokens, acc_balances):
+        eq = is_equal(cs, t, token)
+        delta = mul(cs, eq, amount)
+        nb = b + delta if kind == DEPOSIT else b - delta
+        range_bits(cs, nb, BALANCE_BITS)                            # checked_add / checked_sub
+        matches = matches + eq
+        new_vec += [t, nb]
+    assert_equal(cs, matches, LC.const(1))                          # exactly one token matches
+    assert_equal(cs, poseidon_hash(cs, new_vec), new_account_hash)  # :88-94
+
+
+def synthesize_update_account(w: UpdateAccountWitness) -> ConstraintSystem:
+    """update_account_circuit as an R1CS of its own: instance = (old_account_hash, new_account_hash, amount, token,
+    user) in the field order of UpdateAccountInput's "public inputs" (:23-26), witness = old_account (:29)."""
+    cs = ConstraintSystem()
+    old_h = cs.alloc_input(w.old_account_hash)
+    new_h = cs.alloc_input(w.new_account_hash)
+    amount = cs.alloc_input(w.amount)
+    token = cs.alloc_input(w.token)
+    cs.alloc_input(w.user)
+    acc_tokens, acc_balances = [], []
+    for t, b in zip(w.old_account.tokens, w.old_account.balances):
+        acc_tokens.append(cs.alloc_witness(t)); acc_balances.append(cs.alloc_witness(b))
+    _update_account_gadget(cs, w.kind, amount, token, acc_tokens, acc_balances, old_h, new_h)
+    return cs
+
+
+def account_witness_to_inputs(w: UpdateAccountWitness) -> list:
+    """The 9 field elements of one instance in UpdateAccountInput::new argument order (update_account.rs:37-42)."""
+    return [w.old_account_hash, w.new_account_hash, w.amount, w.token, w.user] + w.old_account.to_vec()
+
+
 def witness_to_inputs(w: UpdateNoteWitness) -> list:
     """The (18 + 2H) field elements of one instance in UpdateNoteInput::new argument order -- the
     input row of b200zk_update_note_witness_batch (include/b200zk.h)."""

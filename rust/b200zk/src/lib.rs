@@ -171,6 +171,7 @@ pub struct GpuProvingKey<'a> {
     gpu: &'a Gpu,
     raw: *mut sys::b200zk_pk,
     r1cs: *mut sys::b200zk_r1cs,
+    tree_height: u32,
 }
 
 /// Upload once; `precompute` stores the window multiples of every query (all windows then share one bucket set).
@@ -195,7 +196,7 @@ pub fn upload_pk<'a>(gpu: &'a Gpu, kind: OpKind, tree_height: u32, pk: &ProvingK
             b1.as_ptr(), b2.as_ptr(), l.as_ptr(), h.as_ptr(), precompute as i32, &mut raw,
         )
     })?;
-    Ok(GpuProvingKey { gpu, raw, r1cs })
+    Ok(GpuProvingKey { gpu, raw, r1cs, tree_height })
 }
 
 impl Drop for GpuProvingKey<'_> {
@@ -213,6 +214,8 @@ impl Drop for GpuProvingKey<'_> {
 pub fn create_proofs(pk: &GpuProvingKey, inputs: &[Fr], batch: usize, r: &[Fr], s: &[Fr]) -> Result<Vec<Proof<Bls12_381>>, SynthesisError> {
     assert_eq!(r.len(), batch);
     assert_eq!(s.len(), batch);
+    // the C side reads batch * (18 + 2 * tree_height) elements: a short slice must never reach it
+    assert_eq!(inputs.len(), batch * (18 + 2 * pk.tree_height as usize), "inputs: batch rows of 18 + 2 * tree_height elements");
     let (rb, sb) = (bigint_bytes(r), bigint_bytes(s));
     let mut out = vec![0u8; batch * 192];
     let rc = unsafe {
@@ -241,6 +244,10 @@ pub fn create_random_proofs<R: RngCore>(pk: &GpuProvingKey, inputs: &[Fr], batch
 /// `Groth16::verify_proof` for a batch: one verdict per proof (`true` = accepted); the place of the mock
 /// `ZkProof::verify_update` (shielder/mocked_zk/src/relations.rs:127-155).
 pub fn verify_proofs(gpu: &Gpu, vk: &VerifyingKey<Bls12_381>, proofs: &[Proof<Bls12_381>], public_inputs: &[Fr]) -> Result<Vec<bool>, Error> {
+    // the C side reads proofs.len() * (gamma_abc_g1.len() - 1) elements
+    if public_inputs.len() != proofs.len() * (vk.gamma_abc_g1.len() - 1) {
+        return Err(Error { code: sys::B200ZK_ERR_BAD_LEN, message: "public_inputs: one row of num_inputs - 1 elements per proof".into() });
+    }
     let mut vkb = Vec::new();
     vk.serialize_compressed(&mut vkb).expect("vk bytes");
     let mut raw = core::ptr::null_mut();

@@ -159,3 +159,103 @@ def test_deposit_relation_proves(ctx):
     assert bytes(proofs) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, cs.z, 77, 99))
     assert og.verify_with_vk(og.verifying_key_from_toxic(sc, TOX), w.public_inputs(), og.proof_from_bytes(bytes(proofs)))
     pk.free()
+
+
+# ----------------------------------------------------------------------------- update-account as a relation of its own
+@pytest.mark.parametrize("kind", [rel.WITHDRAW, rel.DEPOSIT])
+def test_update_account_witness_matches_oracle(ctx, kind):
+    """K6 for update_account_circuit (update_account.rs:68-95): the assignment equals the oracle's synthesis; wrong
+    hashes, an overdraw, a token the account does not hold and an unreduced word are reported per instance."""
+    relation = z.UpdateAccountRelation(kind)
+    ws = [rel.make_account_witness(20 + i, kind) for i in range(5)]
+    rows = [rel.account_witness_to_inputs(w) for w in ws]
+    out, status = relation.witness_batch(ctx, util.fr_mont_array([v for r_ in rows for v in r_]), len(ws))
+    assert list(status) == [0] * len(ws)
+    nv = relation.num_variables
+    for i, w in enumerate(ws):
+        cs = rel.synthesize_update_account(w)
+        assert cs.is_satisfied() and cs.num_variables == nv
+        assert util.fr_from_mont_array(out[i * nv * 32:(i + 1) * nv * 32]) == cs.z
+    good = rows[0]
+    bad_old = list(good); bad_old[0] = (bad_old[0] + 1) % R
+    bad_new = list(good); bad_new[1] = (bad_new[1] + 1) % R
+    bad_tok = list(good); bad_tok[3] = (bad_tok[3] + 1) % R
+    big = list(good); big[2] = 1 << 128
+    arr = util.fr_mont_array(good + bad_old + bad_new + bad_tok + big + good).copy().reshape(6, 9, 32)
+    arr[5, 6] = np.frombuffer(R.to_bytes(32, "little"), dtype=np.uint8)       # balance0 = the word r
+    _, status = relation.witness_batch(ctx, arr.reshape(-1), 6)
+    assert list(status) == [0, 1, 1, 1, 1, 1]
+    relation.free()
+
+
+def test_update_account_proofs_bit_exact_and_verify(ctx):
+    """Key generation, witness generation and proving for the standalone update-account relation: proof bytes equal
+    the oracle's for fixed (r, s) and satisfy the pairing equation against the oracle's verifying key."""
+    relation = z.UpdateAccountRelation(rel.WITHDRAW)
+    pk = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
+                                                        precompute=True)
+    ws = [rel.make_account_witness(50 + i, rel.WITHDRAW) for i in range(3)]
+    cs0 = rel.synthesize_update_account(ws[0])
+    M = cs0.matrices()
+    sc = og.setup_scalars(M, cs0.num_inputs, cs0.num_variables, TOX)
+    inputs = util.fr_mont_array([v for w in ws for v in rel.account_witness_to_inputs(w)])
+    rs, ss = [11, 0, 0x1234567890abcdef], [13, 0, 0xfedcba0987654321]
+    proofs, status = z.Groth16.prove_update_note(pk, inputs, rs, ss, 3)
+    assert list(status) == [0, 0, 0]
+    vk = og.verifying_key_from_toxic(sc, TOX)
+    for i, w in enumerate(ws):
+        zz = rel.synthesize_update_account(w).z
+        pb = bytes(proofs[i * 192:(i + 1) * 192])
+        assert pb == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, zz, rs[i], ss[i]))
+        assert og.verify_with_vk(vk, w.public_inputs(), og.proof_from_bytes(pb))
+    wrong = ws[0].public_inputs(); wrong[1] = (wrong[1] + 1) % R
+    assert not og.verify_with_vk(vk, wrong, og.proof_from_bytes(bytes(proofs[:192])))
+    # a key of the other relation is refused, not misused
+    note_rel = z.UpdateNoteRelation(rel.WITHDRAW, 4)
+    with pytest.raises((z.B200zkError, ValueError)):
+        z.Groth16.prove_update_note(z.ProvingKey(ctx, note_rel, pk._h, None), inputs, rs, ss, 3)
+    pk.free()
+
+
+@pytest.mark.parametrize("height", [4, 20])
+def test_update_note_proves_at_other_tree_heights(ctx, height):
+    """TREE_HEIGHT is a const generic in the reference (merkle_proof.rs:11; the mock fixes 10): witness, key and proof
+    at another depth, bit-exact against the oracle and pairing-verified."""
+    relation = z.UpdateNoteRelation(rel.WITHDRAW, height)
+    pk = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
+                                                        precompute=False)
+    w = rel.make_witness(90 + height, rel.WITHDRAW, height)
+    cs = rel.synthesize_update_note(w, height)
+    assert cs.is_satisfied()
+    M = cs.matrices()
+    sc = og.setup_scalars(M, cs.num_inputs, cs.num_variables, TOX)
+    inputs = util.fr_mont_array(rel.witness_to_inputs(w))
+    out, status = relation.witness_batch(ctx, inputs, 1)
+    assert list(status) == [0] and util.fr_from_mont_array(out) == cs.z
+    proofs, status = z.Groth16.prove_update_note(pk, inputs, [5], [6], 1)
+    assert bytes(proofs) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, cs.z, 5, 6))
+    assert og.verify_with_vk(og.verifying_key_from_toxic(sc, TOX), w.public_inputs(), og.proof_from_bytes(bytes(proofs)))
+    pk.free()
+
+
+def test_create_random_proof_draws_r_then_s(ctx, withdraw_key):
+    """ark_groth16 `create_random_proof_with_reduction(circuit, pk, rng)` draws r, then s, from the caller's RNG and calls
+    create_proof_with_reduction: the host mirror must consume the RNG in that order and produce a valid proof."""
+    relation, pk, M, sc = withdraw_key
+    w = rel.make_witness(123, rel.WITHDRAW)
+    inputs = util.fr_mont_array(rel.witness_to_inputs(w))
+
+    class CountingRng:
+        def __init__(self):
+            self.drawn = []
+        def fr(self):
+            v = (0x9E3779B97F4A7C15 * (len(self.drawn) + 1)) % R
+            self.drawn.append(v)
+            return v
+
+    rng = CountingRng()
+    proof = z.Groth16.create_random_proof(pk, inputs, rng)
+    assert len(rng.drawn) == 2
+    zz = rel.synthesize_update_note(w).z
+    assert bytes(proof) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, zz, rng.drawn[0], rng.drawn[1]))   # r first, s second
+    assert og.verify_with_vk(og.verifying_key_from_toxic(sc, TOX), w.public_inputs(), og.proof_from_bytes(bytes(proof)))

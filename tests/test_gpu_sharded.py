@@ -111,15 +111,81 @@ def _nccl_worker(rank, world, port, out_dir):
         want, _ = z.VariableBaseMSM.msm_bigint(ctx, 1, pts, ss)
         lo, hi = sharded.shard_range(n, rank, world)
         bases = z.VariableBaseMSM.Bases(ctx, 1, pts[lo * 96:hi * 96].copy())
-        m = sharded.ShardedMSM(sharded.GpuBackend(ctx), 1, bases, n, dist)
-        assert m.msm(ss[lo * 32:hi * 32].copy()) == want
+        be = sharded.GpuBackend(ctx, dist)                       # b200zk_comm_init: NCCL id from rank 0 through `dist`
+        assert ctx.comm_info() == (rank, world)
+        m = sharded.ShardedMSM(be, 1, bases, n, dist)
+        assert m.msm(ss[lo * 32:hi * 32].copy()) == want           # b200zk_msm_sharded (host scalars)
+        d_s = ctx.alloc((hi - lo) * 32); ctx.upload(d_s, ss[lo * 32:hi * 32].copy())
+        d_o = ctx.alloc(96)
+        ctx.msm_sharded_device(bases, d_s, hi - lo, d_o)           # asynchronous form, result stays on the device
+        ctx.sync()
+        assert bytes(ctx.download(d_o, 96)) == want
+        ctx.free(d_s); ctx.free(d_o)
         bases.free()
+        # uneven slices incl. an EMPTY one, G2
+        n2 = 41
+        ks2 = util.rand_fr_bytes_fast(7, n2); pts2 = ctx.fixed_base_mul(2, ks2); ss2 = util.rand_fr_bytes_fast(8, n2)
+        want2, _ = z.VariableBaseMSM.msm_bigint(ctx, 2, pts2, ss2)
+        lo2, hi2 = (0, n2) if rank == 0 else (n2, n2)
+        b2 = z.VariableBaseMSM.Bases(ctx, 2, pts2[lo2 * 192:hi2 * 192].copy() if hi2 > lo2 else np.zeros(0, dtype=np.uint8))
+        got2, _ = ctx.msm_sharded(b2, scalars=ss2[lo2 * 32:hi2 * 32].copy(), n=hi2 - lo2)
+        assert got2 == want2
+        b2.free()
         for log_n in (2, 9, 16, 21):
-            _sharded_ntt_check(ctx, sharded.GpuBackend(ctx), dist, rank, world, log_n, 60 + log_n)
+            _sharded_ntt_check(ctx, be, dist, rank, world, log_n, 60 + log_n)
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
         ctx.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_init_multi_and_msm_sharded_multi(ctx):
+    """Single-process form (b200zk_init_multi + b200zk_msm_sharded_multi): one host thread drives every GPU of the box.
+    Runs over however many GPUs are visible (1 on the default test box: no NCCL needed then)."""
+    import ctypes as C
+    import torch
+    G = min(torch.cuda.device_count(), 2)
+    L = z.lib()
+    ctxs = (C.c_void_p * G)()
+    assert L.b200zk_init_multi(G, ctxs) == 0
+    try:
+        n = 777
+        ks = util.rand_fr_bytes_fast(15, n); pts = ctx.fixed_base_mul(1, ks); ss = util.rand_fr_bytes_fast(16, n)
+        want, _ = z.VariableBaseMSM.msm_bigint(ctx, 1, pts, ss)
+        hs, keep, ptrs, ns = (C.c_void_p * G)(), [], (C.c_void_p * G)(), (C.c_size_t * G)()
+        for g in range(G):
+            lo, hi = sharded.shard_range(n, g, G)
+            h = C.c_void_p()
+            pb = np.ascontiguousarray(pts[lo * 96:hi * 96]); sb = np.ascontiguousarray(ss[lo * 32:hi * 32])
+            keep += [pb, sb]
+            assert L.b200zk_bases_upload(ctxs[g], 1, pb.ctypes.data_as(C.c_void_p), None, hi - lo, 0, C.byref(h)) == 0
+            hs[g], ptrs[g], ns[g] = h, sb.ctypes.data, hi - lo
+        out = np.zeros(96, dtype=np.uint8)
+        inf = C.c_uint8()
+        rc = L.b200zk_msm_sharded_multi(ctxs, G, hs, ptrs, 0, ns, out.ctypes.data_as(C.c_void_p), C.byref(inf))
+        assert rc == 0, L.b200zk_last_error(ctxs[0])
+        assert out.tobytes() == want and not inf.value
+        for g in range(G):
+            L.b200zk_bases_free(ctxs[g], hs[g])
+    finally:
+        for g in range(G):
+            L.b200zk_destroy(ctxs[g])
+
+
+def test_sharded_entry_points_without_communicator(ctx):
+    """world == 1 needs no NCCL: the sharded entry points degenerate to the local ones; a ctx that was told it is
+    one rank of several but has no communicator refuses."""
+    n = 300
+    ks = util.rand_fr_bytes_fast(25, n); pts = ctx.fixed_base_mul(1, ks); ss = util.rand_fr_bytes_fast(26, n)
+    want, _ = z.VariableBaseMSM.msm_bigint(ctx, 1, pts, ss)
+    bases = z.VariableBaseMSM.Bases(ctx, 1, pts)
+    assert ctx.comm_info() == (0, 1)
+    assert ctx.msm_sharded(bases, scalars=ss)[0] == want
+    ctx.comm_init(None, 0, 1)
+    assert ctx.msm_sharded(bases, scalars=ss)[0] == want
+    with pytest.raises(z.B200zkError):
+        ctx.comm_init(None, 0, 2)                                   # world 2 without an id
+    bases.free()
 
 
 def test_sharded_msm_world2_nccl(tmp_path):

@@ -117,6 +117,45 @@ def test_update_note_r1cs_other_heights(z):
         r.free()
 
 
+def _diff_r1cs(r, cs):
+    assert (r.num_constraints, r.num_inputs, r.num_variables) == (cs.num_constraints, cs.num_inputs, cs.num_variables)
+    for which, M in enumerate(cs.matrices()):
+        rp, cols, vals = r.matrix(which)
+        assert int(rp[-1]) == sum(len(row) for row in M) == r.nnz[which]
+        vals = bytes(vals)
+        k = 0
+        for i, row in enumerate(M):
+            assert int(rp[i]) == k
+            got = {int(cols[k + j]): bls.fr_from_mont_bytes(vals[32 * (k + j):32 * (k + j + 1)]) for j in range(len(row))}
+            want = {c: v % R for c, v in (row.items() if isinstance(row, dict) else row)}
+            assert got == want, (which, i)
+            k += len(row)
+
+
+@pytest.mark.parametrize("kind", [rel.DEPOSIT, rel.WITHDRAW])
+def test_update_account_r1cs_matches_oracle(z, kind):
+    """b200zk_update_account_r1cs: update_account_circuit (update_account.rs:68-95) as a relation of its own, every
+    matrix entry against the oracle's synthesis; the oracle's own assignment satisfies it."""
+    w = rel.make_account_witness(3, kind)
+    cs = rel.synthesize_update_account(w)
+    assert cs.is_satisfied() and cs.num_inputs == 6
+    r = z.UpdateAccountRelation(kind)
+    _diff_r1cs(r, cs)
+    assert r.n_inputs_per_proof == 9 == len(rel.account_witness_to_inputs(w))
+    r.free()
+
+
+@pytest.mark.parametrize("height", [1, 4, 20])
+def test_update_note_r1cs_matrices_at_other_heights(z, height):
+    """TREE_HEIGHT is a const generic in the reference (merkle_proof.rs:11): full matrix diff away from the mock's 10."""
+    w = rel.make_witness(2, rel.WITHDRAW, height)
+    cs = rel.synthesize_update_note(w, height)
+    assert cs.is_satisfied()
+    r = z.UpdateNoteRelation(rel.WITHDRAW, height)
+    _diff_r1cs(r, cs)
+    r.free()
+
+
 def test_poseidon_constants_match_oracle(z):
     rc, mds = z.poseidon_constants()
     want_rc, want_mds = pos.constants()

@@ -175,3 +175,28 @@ def test_relation_rejects_bad_witnesses():
         else:
             b.path[0] = (b.path[0] + 1) % R
         assert not rel.synthesize_update_note(b).is_satisfied(), mutate
+
+
+def test_poseidon_generator_and_permutation_match_the_public_bn254_instance():
+    """Third-party pin of the Poseidon constants generator (Grain LFSR, rejection sampling, Cauchy MDS from xs + ys)
+    and of the permutation's round structure: for the public instance x5_254_3 (BN254 scalar field, t = 3, R_F = 8,
+    R_P = 57 -- the one circomlib / iden3 ship) the same code must reproduce the published numbers.  None of the
+    literals below comes from this repository: they are the first round constants and MDS entries of
+    poseidonperm_x5_254_3 / circomlib's poseidon_constants and circomlibjs' test vector poseidon([1, 2]).  The
+    shielder instance (BLS12-381 Fr, t = 5, R_P = 56) runs through exactly the same generator and permutation code
+    (oracle/pyref/poseidon.py: constants(), permute_params()), and the C++ generator of the product
+    (csrc/host_r1cs.hpp) is diffed against this one in tests/test_host.py."""
+    from oracle.pyref import poseidon as pos
+    p_bn = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rc, mds = pos.constants(3, 8, 57, p_bn, 254)
+    assert rc[0][0] == 0x0ee9a592ba9a9518d05986d656f40c2114c4993c11bb29938d21d47304cd8e6e
+    assert rc[0][1] == 0x00f1445235f2148c5986587169fc1bcd887b08d4d00868df5696fff40956e864
+    assert rc[0][2] == 0x08dff3487e8ac99e1f29a058d0fa80b930c728730b7ab36ce879f3890ecf73f5
+    assert mds[0][0] == 0x109b7f411ba0e4c9b2b70caf5c36a7b194be7c11ad24378bfedb68592ba8118b
+    assert mds[0][1] == 0x16ed41e13bb9c0c66ae119424fddbcbc9314dc9fdbdeea55d6c64543dc4903e0
+    assert mds[0][2] == 0x2b90bba00fca0589f617e7dcbfe82e0df706ab640ceb247b791a93b74e36736d
+    assert len(rc) == 65 and all(len(r) == 3 for r in rc)
+    # circomlib: state = [0, inputs...], digest = state[0] after the permutation
+    out = pos.permute_params([0, 1, 2], 3, 8, 57, p_bn, 254)
+    assert out[0] == 7853200120776062878684798364095072458815029376092732009249414926327459813530
+    assert out[0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a

@@ -27,7 +27,7 @@ if world > 1:
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     d = dist
 ctx = z.Context(local)
-be = sharded.GpuBackend(ctx)
+be = sharded.GpuBackend(ctx, d)
 pt = 96 if args.group == 1 else 192
 
 

@@ -24,7 +24,7 @@ if world > 1:
     dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     d = dist
 ctx = z.Context(local)
-be = sharded.GpuBackend(ctx)
+be = sharded.GpuBackend(ctx, d)
 
 for lg in [int(x) for x in args.sizes.split(",") if x]:
     n = 1 << lg

@@ -6,6 +6,6 @@ fails loudly if the CUDA library is missing, and creating a Context fails withou
 """
 from .ffi import (B200zkError, Context, lib, lib_path, Radix2EvaluationDomain, VariableBaseMSM,  # noqa: F401
                   FR_BYTES, G1_BYTES, G2_BYTES, fr_to_mont, fr_from_mont, STATUS, DEPOSIT, WITHDRAW,
-                  poseidon_constants, poseidon_hash_batch, UpdateNoteRelation, ProvingKey, VerifyingKey, Groth16, MerkleTree,
+                  poseidon_constants, poseidon_hash_batch, UpdateNoteRelation, UpdateAccountRelation, ProvingKey, VerifyingKey, Groth16, MerkleTree,
                   points_compress, points_decompress, PROOF_STATUS)
 from . import ffi, sharded  # noqa: F401,E402

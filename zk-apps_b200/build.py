@@ -50,7 +50,7 @@ def build_cuda(verbose: bool = False) -> str:
             if verbose and out:
                 print(out)
     if jobs or not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest(objs):
-        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart_static"])
+        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart_static", "-ldl"])
     return LIB
 
 

@@ -41,7 +41,8 @@ struct b200zk_ctx {
     bool msm_glv = true;                                   // b200zk_set_option("msm_glv"): GLV for plain G1 bases
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
-    std::map<uint64_t, b200zk::DeviceBuf> tables;          // twiddle / coset tables, keyed
+    std::map<std::string, b200zk::DeviceBuf> tables;       // twiddle / coset tables; the key spells out kind, size and
+                                                           // the full 32-byte base (no hash: nothing to collide)
     // profiling (b200zk_prof_*): when enabled every launch of a tracked kernel is bracketed by
     // events on ctx->stream; resolved lazily at b200zk_prof_get.
     bool prof_enabled = false;
@@ -53,6 +54,8 @@ struct b200zk_ctx {
     long launches = 0;                                     // every kernel launch of this library
     std::map<std::string, double> stats;                   // work counters (b200zk_stat_get)
     void* poseidon_consts = nullptr;                       // device copy, see poseidon.cu
+    void* nccl_comm = nullptr;                             // ncclComm_t of this rank (csrc/comm.cu), null without one
+    int comm_rank = 0, comm_world = 1;
 };
 
 namespace b200zk {

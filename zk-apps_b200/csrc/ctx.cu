@@ -83,6 +83,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    b200zk_comm_destroy(ctx);
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -125,7 +126,12 @@ int b200zk_dev_alloc(b200zk_ctx* ctx, size_t bytes, void** dptr) {
 
 int b200zk_dev_free(b200zk_ctx* ctx, void* dptr) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // work on any stream of the ctx may still read the buffer (auxiliary MSM streams, assembly streams)
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->aux[i]));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->fin));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->fin2));
     B200ZK_CUDA(ctx, cudaFree(dptr));
     return B200ZK_OK;
 }

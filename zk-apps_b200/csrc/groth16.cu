@@ -27,7 +27,9 @@ struct Csr {
 struct b200zk_pk {
     uint32_t num_constraints = 0, num_inputs = 0, num_aux = 0, log_n = 0;
     int kind = 0;
+    int relation = 0;                  // host::RELATION_UPDATE_NOTE / _ACCOUNT: which witness generator feeds this key
     uint32_t tree_height = 0;
+    uint32_t inputs_per_instance = 0;  // Fr elements per input row of that witness generator
     Csr m[3];
     b200zk_bases a_query, b_g1_query, b_g2_query, l_query, h_query;
     G1Affine alpha_g1, beta_g1, delta_g1;
@@ -318,7 +320,9 @@ int pk_common(b200zk_ctx* ctx, const b200zk_r1cs* r, b200zk_pk* pk) {
     pk->num_inputs = cs.num_inputs;
     pk->num_aux = cs.num_aux;
     pk->kind = cs.kind;
+    pk->relation = cs.relation;
     pk->tree_height = cs.tree_height;
+    pk->inputs_per_instance = cs.inputs_per_instance;
     uint32_t lg = 0;
     while ((1ull << lg) < (uint64_t)pk->num_constraints + pk->num_inputs) lg++;
     pk->log_n = lg;
@@ -789,12 +793,13 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
 
 static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, int inputs_on_device,
                                   size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
-                                  uint8_t* out_status) {
+                                  uint8_t* out_status, int relation = host::RELATION_UPDATE_NOTE) {
     if (!ctx || !pk || !inputs || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
+    if (pk->relation != relation) return fail(ctx, B200ZK_ERR_BAD_ARG, "the proving key belongs to the other relation");
     if (batch == 0) return B200ZK_OK;
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t H = pk->tree_height, nv = pk->num_inputs + pk->num_aux;
-    const size_t in_bytes = batch * (18 + 2 * (size_t)H) * 32;
+    const size_t in_bytes = batch * (size_t)pk->inputs_per_instance * 32;
     void *din = (void*)inputs, *dz, *dst;
     if (!inputs_on_device) B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
     B200ZK_TRY(scratch(ctx, "g16_z", batch * (size_t)nv * sizeof(Fr), &dz));
@@ -802,7 +807,7 @@ static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const ui
     if (!inputs_on_device)
         B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_TRY(groth16_prove_begin(ctx, pk, batch, r, s));
-    B200ZK_TRY(update_note_witness_device(ctx, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
+    B200ZK_TRY(relation_witness_device(ctx, pk->relation, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
     std::vector<uint32_t> st(batch);
     B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -813,13 +818,18 @@ static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const ui
         bad = bad || (st[i] & 1);
     }
     // like arkworks, an unsatisfied instance is an error, not a proof (SynthesisError::Unsatisfiable in debug builds)
-    if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the update-note relation");
+    if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the relation");
     return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, proofs_out, nullptr);
 }
 
 int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
                                    const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {
     return prove_update_note_impl(ctx, pk, inputs, 0, batch, r, s, proofs_out, out_status);
+}
+
+int b200zk_update_account_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
+                                      const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {
+    return prove_update_note_impl(ctx, pk, inputs, 0, batch, r, s, proofs_out, out_status, host::RELATION_UPDATE_ACCOUNT);
 }
 
 int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,

@@ -29,6 +29,7 @@ constexpr int POSEIDON_SBOXES = POSEIDON_RF * POSEIDON_T + POSEIDON_RP;  // 96
 constexpr int POSEIDON_TRACE = POSEIDON_SBOXES * 3;                      // witnesses per permutation
 constexpr int BALANCE_BITS = 128;
 constexpr int KIND_DEPOSIT = 0, KIND_WITHDRAW = 1;
+constexpr int RELATION_UPDATE_NOTE = 0, RELATION_UPDATE_ACCOUNT = 1;
 
 struct PoseidonConsts {
     Fr rc[POSEIDON_ROUNDS][POSEIDON_T];
@@ -204,7 +205,9 @@ struct R1CS {
     uint32_t num_aux = 0;
     std::vector<LC> A, B, C;
     int kind = KIND_WITHDRAW;
+    int relation = 0;         // RELATION_UPDATE_NOTE / RELATION_UPDATE_ACCOUNT
     uint32_t tree_height = 0;
+    uint32_t inputs_per_instance = 0;  // Fr elements of one input row of the witness generator
 
     uint32_t num_variables() const { return num_inputs + num_aux; }
     LC alloc_input() { return LC::var(num_inputs++); }
@@ -278,12 +281,39 @@ inline LC g_poseidon_hash(R1CS& cs, const std::vector<LC>& in) {  // PoseidonHas
     return s[1];
 }
 
+// update_account_circuit (update_account.rs:68-95) with the mock's concrete Account / Operation: verify_account_circuit
+// on the old account (:79-85), `update` (account.rs:36-79 of the mock: the balance whose token matches moves by
+// `amount`, checked_add / checked_sub as 128-bit range checks, exactly one token must match), verify_account_circuit
+// on the new one (:88-94).  Shared by the standalone relation and by update_note_circuit, which calls it as its last
+// step (update_note.rs:141-148) -- the witness kernels allocate in exactly this order.
+inline void g_update_account(R1CS& cs, int kind, const LC& amount, const LC& token, const LC acc_token[2],
+                             const LC acc_balance[2], const LC& old_account_hash, const LC& new_account_hash) {
+    std::vector<LC> old_vec = {acc_token[0], acc_balance[0], acc_token[1], acc_balance[1]};
+    g_assert_equal(cs, g_poseidon_hash(cs, old_vec), old_account_hash);
+    g_range_bits(cs, amount, BALANCE_BITS);
+    LC matches;
+    std::vector<LC> new_vec;
+    for (int i = 0; i < 2; i++) {
+        LC eq = g_is_zero(cs, acc_token[i] - token);
+        LC delta = g_mul(cs, eq, amount);
+        LC nb = kind == KIND_DEPOSIT ? acc_balance[i] + delta : acc_balance[i] - delta;
+        g_range_bits(cs, nb, BALANCE_BITS);
+        matches = matches + eq;
+        new_vec.push_back(acc_token[i]);
+        new_vec.push_back(nb);
+    }
+    g_assert_equal(cs, matches, LC::constant(Fr::one()));
+    g_assert_equal(cs, g_poseidon_hash(cs, new_vec), new_account_hash);
+}
+
 // update_note_circuit as R1CS.  Must stay in lock-step with update_note_witness_kernel (relation.cu):
 // both allocate witnesses in exactly this order.
 inline R1CS synthesize_update_note(int kind, uint32_t tree_height) {
     R1CS cs;
     cs.kind = kind;
+    cs.relation = RELATION_UPDATE_NOTE;
     cs.tree_height = tree_height;
+    cs.inputs_per_instance = 18 + 2 * tree_height;
     // instance variables (make_public order, update_note.rs:121,127)
     LC amount = cs.alloc_input(), token = cs.alloc_input(), user = cs.alloc_input();
     LC new_note_hash = cs.alloc_input(), merkle_root = cs.alloc_input(), old_nullifier = cs.alloc_input();
@@ -315,23 +345,31 @@ inline R1CS synthesize_update_note(int kind, uint32_t tree_height) {
     g_assert_equal(cs, current, merkle_root);
     // CircuitOperation::combine(op_priv, op_pub).unwrap()           update_note.rs:139
     g_assert_equal(cs, user, op_priv_user);
-    // update_account_circuit                                        update_account.rs:68-95
-    std::vector<LC> old_vec = {acc_token[0], acc_balance[0], acc_token[1], acc_balance[1]};
-    g_assert_equal(cs, g_poseidon_hash(cs, old_vec), old_account_hash);
-    g_range_bits(cs, amount, BALANCE_BITS);
-    LC matches;
-    std::vector<LC> new_vec;
+    // update_account_circuit                                        update_note.rs:141-148 -> update_account.rs:68-95
+    g_update_account(cs, kind, amount, token, acc_token, acc_balance, old_account_hash, new_note[3]);
+    return cs;
+}
+
+// update_account_circuit as a relation of its own (update_account.rs:68-95; UpdateAccountInput :18-30).
+// Instance variables in the struct's field order ("public inputs", :23-26): old_account_hash, new_account_hash,
+// operation = (amount, token, user) -- the operation arrives already combined (A::Op), so `user` is carried as an
+// instance variable without a constraint of its own, like every other field `update` does not look at.
+// Witness: old_account (:29) = (token0, balance0, token1, balance1).  Lock-step with update_account_witness_kernel.
+inline R1CS synthesize_update_account(int kind) {
+    R1CS cs;
+    cs.kind = kind;
+    cs.relation = RELATION_UPDATE_ACCOUNT;
+    cs.tree_height = 0;
+    cs.inputs_per_instance = 9;
+    LC old_account_hash = cs.alloc_input(), new_account_hash = cs.alloc_input();
+    LC amount = cs.alloc_input(), token = cs.alloc_input(), user = cs.alloc_input();
+    (void)user;
+    LC acc_token[2], acc_balance[2];
     for (int i = 0; i < 2; i++) {
-        LC eq = g_is_zero(cs, acc_token[i] - token);
-        LC delta = g_mul(cs, eq, amount);
-        LC nb = kind == KIND_DEPOSIT ? acc_balance[i] + delta : acc_balance[i] - delta;
-        g_range_bits(cs, nb, BALANCE_BITS);
-        matches = matches + eq;
-        new_vec.push_back(acc_token[i]);
-        new_vec.push_back(nb);
+        acc_token[i] = cs.alloc_witness();
+        acc_balance[i] = cs.alloc_witness();
     }
-    g_assert_equal(cs, matches, LC::constant(Fr::one()));
-    g_assert_equal(cs, g_poseidon_hash(cs, new_vec), new_note[3]);
+    g_update_account(cs, kind, amount, token, acc_token, acc_balance, old_account_hash, new_account_hash);
     return cs;
 }
 

@@ -32,6 +32,7 @@ struct b200zk_merkle {
     Fr* d_nodes = nullptr;       // 2 * size
     bool log_roots = false;
     std::set<std::array<uint8_t, 32>> roots_log;
+    bool poisoned = false;       // a CUDA call failed in the middle of add_leaves: device nodes and host state disagree
 };
 
 namespace {
@@ -256,24 +257,14 @@ int b200zk_merkle_info(const b200zk_merkle* t, uint32_t* depth, uint64_t* size, 
     return B200ZK_OK;
 }
 
-int b200zk_merkle_add_leaves(b200zk_ctx* ctx, b200zk_merkle* t, const void* leaves, int on_device, size_t n,
-                             uint64_t* first_leaf_id, uint8_t* roots_out) {
-    if (!ctx || !t || (!leaves && n)) return B200ZK_ERR_BAD_ARG;
-    if (first_leaf_id) *first_leaf_id = t->next_leaf_idx;
-    if (n == 0) return B200ZK_OK;
-    if (n > t->size - t->next_leaf_idx)                                   // merkle.rs:49-51
-        return fail(ctx, B200ZK_ERR_MERKLE_LIMIT_EXCEEDED, "MerkleTreeLimitExceeded: the leaves do not fit (none was added)");
-    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const PoseidonConsts* pc;
-    B200ZK_TRY(poseidon_consts_device(ctx, &pc));
+// the part of add_leaves that mutates the tree; any failure in here leaves it inconsistent (caller poisons it)
+static int add_leaves_mutate(b200zk_ctx* ctx, b200zk_merkle* t, const void* leaves, int on_device, size_t n,
+                             const PoseidonConsts* pc, void* d_roots, uint8_t* roots_dst) {
     const uint64_t first = t->next_leaf_idx;
     B200ZK_CUDA(ctx, cudaMemcpyAsync(t->d_nodes + t->size + first, leaves, n * sizeof(Fr),
                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_TRY(rebuild_levels(ctx, t, first, n, pc));
-    t->next_leaf_idx += n;
-    if (t->log_roots || roots_out) {
-        void* d_roots;
-        B200ZK_TRY(scratch(ctx, "merkle_roots", n * sizeof(Fr), &d_roots));
+    if (d_roots) {
         {
             ProfScope ps(ctx, "merkle_roots");
             if (n <= WARP_PATH_MAX)
@@ -284,28 +275,58 @@ int b200zk_merkle_add_leaves(b200zk_ctx* ctx, b200zk_merkle* t, const void* leav
                                                                              (Fr*)d_roots);
         }
         B200ZK_TRY(check_launch(ctx, "merkle_roots_kernel"));
-        std::vector<uint8_t> tmp;
-        uint8_t* dst = roots_out;
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(roots_dst, d_roots, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // also: the host buffer `leaves` is the caller's again
+    return B200ZK_OK;
+}
+
+int b200zk_merkle_add_leaves(b200zk_ctx* ctx, b200zk_merkle* t, const void* leaves, int on_device, size_t n,
+                             uint64_t* first_leaf_id, uint8_t* roots_out) {
+    if (!ctx || !t || (!leaves && n)) return B200ZK_ERR_BAD_ARG;
+    if (t->poisoned) return fail(ctx, B200ZK_ERR_CUDA, "merkle tree unusable: an earlier add_leaves failed part-way");
+    if (first_leaf_id) *first_leaf_id = t->next_leaf_idx;
+    if (n == 0) return B200ZK_OK;
+    if (n > t->size - t->next_leaf_idx)                                   // merkle.rs:49-51
+        return fail(ctx, B200ZK_ERR_MERKLE_LIMIT_EXCEEDED, "MerkleTreeLimitExceeded: the leaves do not fit (none was added)");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // "all or nothing": everything that can fail without the device being lost (constant upload, scratch and
+    // host allocations) happens BEFORE the first write to the tree
+    const PoseidonConsts* pc;
+    B200ZK_TRY(poseidon_consts_device(ctx, &pc));
+    const bool want_roots = t->log_roots || roots_out;
+    void* d_roots = nullptr;
+    std::vector<uint8_t> tmp;
+    uint8_t* dst = roots_out;
+    if (want_roots) {
+        B200ZK_TRY(scratch(ctx, "merkle_roots", n * sizeof(Fr), &d_roots));
         if (!dst) {
-            tmp.resize(n * 32);
+            try {
+                tmp.resize(n * 32);
+            } catch (...) {
+                return fail(ctx, B200ZK_ERR_BAD_LEN, "merkle_add_leaves: out of host memory for the roots");
+            }
             dst = tmp.data();
         }
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(dst, d_roots, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
-        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (t->log_roots)
-            for (size_t i = 0; i < n; i++) {
-                std::array<uint8_t, 32> r;
-                memcpy(r.data(), dst + i * 32, 32);
-                t->roots_log.insert(r);
-            }
-    } else {
-        B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host buffer `leaves` is the caller's again
     }
+    const int rc = add_leaves_mutate(ctx, t, leaves, on_device, n, pc, d_roots, dst);
+    if (rc != B200ZK_OK) {  // a launch / copy failed on a tree already written to: the CUDA context is gone or the
+        t->poisoned = true; // nodes are half updated; refuse further use instead of serving a wrong root
+        return rc;
+    }
+    t->next_leaf_idx += n;
+    if (t->log_roots)
+        for (size_t i = 0; i < n; i++) {
+            std::array<uint8_t, 32> r;
+            memcpy(r.data(), dst + i * 32, 32);
+            t->roots_log.insert(r);
+        }
     return B200ZK_OK;
 }
 
 int b200zk_merkle_root(b200zk_ctx* ctx, const b200zk_merkle* t, uint8_t out[32]) {
     if (!ctx || !t || !out) return B200ZK_ERR_BAD_ARG;
+    if (t->poisoned) return fail(ctx, B200ZK_ERR_CUDA, "merkle tree unusable: an earlier add_leaves failed part-way");
     if (t->next_leaf_idx == 0)                                            // merkle.rs:42-46: node 1 was never written
         return fail(ctx, B200ZK_ERR_MERKLE_NON_EXISTING_NODE, "MerkleTreeNonExistingNode: the tree is empty");
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -316,6 +337,7 @@ int b200zk_merkle_root(b200zk_ctx* ctx, const b200zk_merkle* t, uint8_t out[32])
 
 int b200zk_merkle_node(b200zk_ctx* ctx, const b200zk_merkle* t, uint64_t id, uint8_t out[32]) {
     if (!ctx || !t || !out || id == 0 || id >= 2 * t->size) return B200ZK_ERR_BAD_ARG;
+    if (t->poisoned) return fail(ctx, B200ZK_ERR_CUDA, "merkle tree unusable: an earlier add_leaves failed part-way");
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(out, t->d_nodes + id, 32, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -314,23 +314,38 @@ Fr host_fr_from_u64(uint64_t v) {
     return fp_to_mont(r);
 }
 
-uint64_t hash_bytes(const uint8_t* b, size_t n) {
-    uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
-    return h;
+// table key: kind, log size, and the bytes that define the contents written out in full
+std::string table_key(const char* kind, uint32_t log_n, const Fr* base = nullptr, int flag = 0) {
+    std::string k = std::string(kind) + ":" + std::to_string(log_n) + ":" + std::to_string(flag);
+    if (base) {
+        static const char* hex = "0123456789abcdef";
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(base);
+        k += ":";
+        for (size_t i = 0; i < sizeof(Fr); i++) {
+            k += hex[b[i] >> 4];
+            k += hex[b[i] & 15];
+        }
+    }
+    return k;
 }
 
-int get_table(b200zk_ctx* ctx, uint64_t key, const Fr& base, const Fr& scale, uint64_t count, const Fr** out) {
-    DeviceBuf& b = ctx->tables[key];
-    if (!b.ptr) {
+int get_table(b200zk_ctx* ctx, const std::string& key, const Fr& base, const Fr& scale, uint64_t count, const Fr** out) {
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        DeviceBuf b;
         size_t bytes = (size_t)(count ? count : 1) * sizeof(Fr);
         B200ZK_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
         b.bytes = bytes;
         pow_table_kernel<<<div_up(count ? count : 1, 256), 256, 0, ctx->stream>>>(base, scale, (Fr*)b.ptr,
                                                                                   count ? count : 1);
-        B200ZK_TRY(check_launch(ctx, "pow_table_kernel"));
+        const int rc = check_launch(ctx, "pow_table_kernel");
+        if (rc != B200ZK_OK) {  // never cache a table that was not written
+            cudaFree(b.ptr);
+            return rc;
+        }
+        it = ctx->tables.emplace(key, b).first;
     }
-    *out = (const Fr*)b.ptr;
+    *out = (const Fr*)it->second.ptr;
     return B200ZK_OK;
 }
 
@@ -348,13 +363,12 @@ int ntt_device(b200zk_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const 
 
     const Fr w = host_root_of_unity(log_n);
     const Fr* tw;
-    B200ZK_TRY(get_table(ctx, (1ull << 56) | log_n, w, Fr::one(), n >> 1, &tw));
+    B200ZK_TRY(get_table(ctx, table_key("tw", log_n), w, Fr::one(), n >> 1, &tw));
     const Fr n_inv = fp_inv(host_fr_from_u64(n));
     const Fr *pre = nullptr, *post = nullptr;
     if (coset) {
-        uint64_t h = hash_bytes((const uint8_t*)coset_offset, sizeof(Fr)) & 0x0000ffffffffff00ull;
-        if (!inverse) B200ZK_TRY(get_table(ctx, (2ull << 56) | h | log_n, *coset_offset, Fr::one(), n, &pre));
-        else B200ZK_TRY(get_table(ctx, (3ull << 56) | h | log_n, fp_inv(*coset_offset), n_inv, n, &post));
+        if (!inverse) B200ZK_TRY(get_table(ctx, table_key("coset_pre", log_n, coset_offset), *coset_offset, Fr::one(), n, &pre));
+        else B200ZK_TRY(get_table(ctx, table_key("coset_post", log_n, coset_offset), fp_inv(*coset_offset), n_inv, n, &post));
     }
 
     // plan
@@ -460,9 +474,8 @@ int b200zk_ntt_twiddle_transpose_device(b200zk_ctx* ctx, const void* d_in, void*
     Fr w_hi = w;
     for (uint32_t i = 0; i < S; i++) w_hi = fp_sqr(w_hi);
     const Fr *t_lo, *t_hi;
-    const uint64_t key = (4ull << 56) | ((uint64_t)(inverse ? 1 : 0) << 40) | ((uint64_t)log_n << 8);
-    B200ZK_TRY(get_table(ctx, key | 0, w, Fr::one(), 1ull << S, &t_lo));
-    B200ZK_TRY(get_table(ctx, key | 1, w_hi, Fr::one(), 1ull << (log_n - S), &t_hi));
+    B200ZK_TRY(get_table(ctx, table_key("tt_lo", log_n, nullptr, inverse ? 1 : 0), w, Fr::one(), 1ull << S, &t_lo));
+    B200ZK_TRY(get_table(ctx, table_key("tt_hi", log_n, nullptr, inverse ? 1 : 0), w_hi, Fr::one(), 1ull << (log_n - S), &t_hi));
     dim3 grid(div_up(cols, TT), div_up(rows, TT));
     {
         ProfScope ps(ctx, "ntt_twiddle_transpose");

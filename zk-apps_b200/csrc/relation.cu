@@ -88,6 +88,73 @@ __device__ __forceinline__ bool fits_bits128(const Fr& canon) {
     return (canon.v[4] | canon.v[5] | canon.v[6] | canon.v[7]) == 0;
 }
 
+// every input word of an instance must be a field element (< r): ark's Fr cannot hold anything else, and the
+// inversions below must never see an unreduced word.  All threads of the CTA call this.
+__device__ __forceinline__ bool inputs_canonical(const Fr* in, uint32_t n_in) {
+    bool canon = true;
+    for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x) {
+        const Fr v = ld_fr(in + i);
+        bool lt = false;  // v < r, most significant limb first
+        for (int k = 7; k >= 0; k--) {
+            if (v.v[k] != FrCfg::mod(k)) {
+                lt = v.v[k] < FrCfg::mod(k);
+                break;
+            }
+        }
+        canon = canon && lt;
+    }
+    return __syncthreads_and(canon ? 1 : 0) != 0;
+}
+
+// Witness block of g_update_account (host_r1cs.hpp), warp-wide: H(old_account) == old_hash, the bits of `amount`,
+// per token slot (inverse-or-0, is_equal, delta, bits of the new balance), H(new_account) == new_hash.
+// acc = (token0, balance0, token1, balance1); zb = first witness of the block.  Returns "all checks hold".
+__device__ bool account_update_witness(const Fr* __restrict__ acc, const Fr& amount, const Fr& token, const Fr& old_hash,
+                                       const Fr& new_hash, int kind, int lane, const PoseidonConsts* pc, Fr* zb) {
+    const uint32_t T = host::POSEIDON_TRACE;
+    Fr* z_old = zb;
+    Fr* z_bits = zb + 2 * T;
+    Fr* z_upd = z_bits + host::BALANCE_BITS;
+    Fr* z_new = z_upd + 2 * (3 + host::BALANCE_BITS);
+    const bool wr = lane == 0;
+    bool ok = true;
+    // ---- H(old_account) == old_hash                                     update_account.rs:79-85
+    Fr h_acc = poseidon_hash_w(4, [&](int i) { return ld_fr(acc + i); }, lane, pc, z_old);
+    ok = ok && (h_acc == old_hash);
+    // ---- account update                                                  account.rs:36-79 (mock)
+    {
+        const Fr canon = fp_from_mont(amount);
+        ok = ok && fits_bits128(canon);
+        for (int b = lane; b < host::BALANCE_BITS; b += 32)
+            st_fr(z_bits + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
+    }
+    Fr new_bal[2];
+    int n_match = 0;
+    for (int i = 0; i < 2; i++) {
+        Fr* zu = z_upd + (size_t)i * (3 + host::BALANCE_BITS);
+        const Fr tok = ld_fr(acc + 2 * i), bal = ld_fr(acc + 2 * i + 1);
+        const Fr diff = fp_sub(tok, token);
+        const bool eq = diff.is_zero();
+        n_match += eq ? 1 : 0;
+        const Fr delta = eq ? amount : Fr::zero();
+        if (wr) {
+            st_fr(zu, eq ? Fr::zero() : fp_inv(diff));
+            st_fr(zu + 1, eq ? Fr::one() : Fr::zero());
+            st_fr(zu + 2, delta);
+        }
+        new_bal[i] = kind == host::KIND_DEPOSIT ? fp_add(bal, delta) : fp_sub(bal, delta);
+        const Fr canon = fp_from_mont(new_bal[i]);
+        ok = ok && fits_bits128(canon);                                // checked_add / checked_sub
+        for (int b = lane; b < host::BALANCE_BITS; b += 32)
+            st_fr(zu + 3 + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
+    }
+    ok = ok && n_match == 1;
+    // ---- H(new_account) == new_hash                                      update_account.rs:88-94
+    Fr h_nacc = poseidon_hash_w(4, [&](int i) { return (i & 1) ? new_bal[i >> 1] : ld_fr(acc + i); }, lane, pc, z_new);
+    ok = ok && (h_nacc == new_hash);
+    return ok;
+}
+
 // inputs per proof, each a Montgomery Fr, in UpdateNoteInput::new argument order:
 //   op_pub (amount, token, user) | new_note_hash | merkle_root | new_note[4] | old_note[4] |
 //   path_shape[H] | path[H] | op_priv.user | old_account (token0, balance0, token1, balance1)
@@ -117,24 +184,11 @@ __global__ void __launch_bounds__(64) update_note_witness_kernel(const Fr* __res
     const uint32_t O_END = O_NACC_HASH + 2 * T;
     const bool wr = lane == 0;  // the lane that writes scalar witnesses
     bool ok = true;
-    {   // Input rows come from the caller unchecked: a word >= r is not a field element (ark's Fr cannot hold one).
-        // Such an instance is reported as unsatisfied and nothing below (inversions included) ever sees it.
-        bool canon = true;
-        for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x) {
-            const Fr v = ld_fr(in + i);
-            bool lt = false;  // v < r, most significant limb first
-            for (int k = 7; k >= 0; k--) {
-                if (v.v[k] != FrCfg::mod(k)) {
-                    lt = v.v[k] < FrCfg::mod(k);
-                    break;
-                }
-            }
-            canon = canon && lt;
-        }
-        if (!__syncthreads_and(canon ? 1 : 0)) {
-            if (threadIdx.x == 0) status[proof] = 1u | (O_END == num_vars ? 0u : 2u);
-            return;
-        }
+    // Input rows come from the caller unchecked: an instance holding a word >= r is reported as unsatisfied and nothing
+    // below (inversions included) ever sees it.
+    if (!inputs_canonical(in, n_in)) {
+        if (threadIdx.x == 0) status[proof] = 1u | (O_END == num_vars ? 0u : 2u);
+        return;
     }
     if (warp == 0) {
         // ---- z[0] = 1, instance variables, loaded witnesses
@@ -182,47 +236,37 @@ __global__ void __launch_bounds__(64) update_note_witness_kernel(const Fr* __res
         // ---- H(new_note) == new_note_hash                               update_note.rs:129
         Fr h_new = poseidon_hash_w(4, [&](int i) { return ld_fr(in + I_NEW + i); }, lane, pc, z + O_NEW_HASH);
         ok = ok && (h_new == ld_fr(in + I_NNH));
-        // ---- H(old_account) == old_note.account_hash                     update_account.rs:79-85
-        Fr h_acc = poseidon_hash_w(4, [&](int i) { return ld_fr(in + I_ACC + i); }, lane, pc, z + O_ACC_HASH);
-        ok = ok && (h_acc == ld_fr(in + I_OLD + 3));
-        // ---- account update                                              account.rs:36-79 (mock)
-        const Fr amount = ld_fr(in + I_AMOUNT);
-        const Fr token = ld_fr(in + I_TOKEN);
-        {
-            const Fr canon = fp_from_mont(amount);
-            ok = ok && fits_bits128(canon);
-            for (int b = lane; b < host::BALANCE_BITS; b += 32)
-                st_fr(z + O_AMOUNT_BITS + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
-        }
-        Fr new_bal[2];
-        int n_match = 0;
-        for (int i = 0; i < 2; i++) {
-            Fr* zu = z + O_UPDATE + (size_t)i * (3 + host::BALANCE_BITS);
-            const Fr tok = ld_fr(in + I_ACC + 2 * i), bal = ld_fr(in + I_ACC + 2 * i + 1);
-            const Fr diff = fp_sub(tok, token);
-            const bool eq = diff.is_zero();
-            n_match += eq ? 1 : 0;
-            const Fr delta = eq ? amount : Fr::zero();
-            if (wr) {
-                st_fr(zu, eq ? Fr::zero() : fp_inv(diff));
-                st_fr(zu + 1, eq ? Fr::one() : Fr::zero());
-                st_fr(zu + 2, delta);
-            }
-            new_bal[i] = kind == host::KIND_DEPOSIT ? fp_add(bal, delta) : fp_sub(bal, delta);
-            const Fr canon = fp_from_mont(new_bal[i]);
-            ok = ok && fits_bits128(canon);                                // checked_add / checked_sub
-            for (int b = lane; b < host::BALANCE_BITS; b += 32)
-                st_fr(zu + 3 + b, ((canon.v[b >> 5] >> (b & 31)) & 1) ? Fr::one() : Fr::zero());
-        }
-        ok = ok && n_match == 1;
-        // ---- H(new_account) == new_note.account_hash                     update_account.rs:88-94
-        Fr h_nacc = poseidon_hash_w(
-            4, [&](int i) { return (i & 1) ? new_bal[i >> 1] : ld_fr(in + I_ACC + i); }, lane, pc, z + O_NACC_HASH);
-        ok = ok && (h_nacc == ld_fr(in + I_NEW + 3));
+        // ---- update_account_circuit                                      update_note.rs:141-148
+        const bool acc_ok = account_update_witness(in + I_ACC, ld_fr(in + I_AMOUNT), ld_fr(in + I_TOKEN), ld_fr(in + I_OLD + 3),
+                                                   ld_fr(in + I_NEW + 3), kind, lane, pc, z + O_ACC_HASH);
+        ok = ok && acc_ok;
     }
     if (wr) ok_sh[warp] = ok ? 1u : 0u;
     __syncthreads();
     if (threadIdx.x == 0) status[proof] = ((ok_sh[0] & ok_sh[1]) ? 0u : 1u) | (O_END == num_vars ? 0u : 2u);
+}
+
+// update_account_circuit as a relation of its own (update_account.rs:68-95): one warp per instance.
+// input row (9 Fr, UpdateAccountInput::new argument order :37-42): old_account_hash | new_account_hash |
+// operation (amount, token, user) | old_account (token0, balance0, token1, balance1)
+__global__ void __launch_bounds__(32) update_account_witness_kernel(const Fr* __restrict__ inputs, uint32_t n, int kind,
+                                                                   uint32_t num_vars, const PoseidonConsts* __restrict__ pc,
+                                                                   Fr* __restrict__ z_all, uint32_t* __restrict__ status) {
+    const uint32_t inst = blockIdx.x;
+    if (inst >= n) return;
+    const int lane = threadIdx.x;
+    const Fr* in = inputs + (size_t)inst * 9;
+    Fr* z = z_all + (size_t)inst * num_vars;
+    const uint32_t T = host::POSEIDON_TRACE;
+    const uint32_t O_END = 10 + 2 * T + host::BALANCE_BITS + 2 * (3 + host::BALANCE_BITS) + 2 * T;
+    if (!inputs_canonical(in, 9)) {
+        if (lane == 0) status[inst] = 1u | (O_END == num_vars ? 0u : 2u);
+        return;
+    }
+    if (lane == 0) st_fr(z, Fr::one());
+    if (lane < 9) st_fr(z + 1 + lane, ld_fr(in + lane));   // 5 instance variables, then the 4 account witnesses
+    const bool ok = account_update_witness(in + 5, ld_fr(in + 2), ld_fr(in + 3), ld_fr(in + 0), ld_fr(in + 1), kind, lane, pc, z + 10);
+    if (lane == 0) status[inst] = (ok ? 0u : 1u) | (O_END == num_vars ? 0u : 2u);
 }
 
 // n_hashes independent hash_fix_len_array calls of the same arity (Merkle tree levels, note hashes)
@@ -268,6 +312,20 @@ int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t n
     return check_launch(ctx, "update_note_witness_kernel");
 }
 
+// witness generation of either relation; d_inputs: batch * inputs_per_instance Fr
+int relation_witness_device(b200zk_ctx* ctx, int relation, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs,
+                            size_t batch, Fr* d_z, uint32_t* d_status) {
+    if (relation == host::RELATION_UPDATE_NOTE) return update_note_witness_device(ctx, kind, H, num_vars, d_inputs, batch, d_z, d_status);
+    const PoseidonConsts* pc;
+    B200ZK_TRY(poseidon_consts_device(ctx, &pc));
+    {
+        ProfScope ps(ctx, "witness");
+        update_account_witness_kernel<<<(unsigned)batch, 32, 0, ctx->stream>>>(d_inputs, (uint32_t)batch, kind, num_vars, pc, d_z,
+                                                                               d_status);
+    }
+    return check_launch(ctx, "update_account_witness_kernel");
+}
+
 }  // namespace b200zk
 
 extern "C" {
@@ -283,6 +341,14 @@ int b200zk_update_note_r1cs(int kind, uint32_t tree_height, b200zk_r1cs** out) {
     if (!out || (kind != 0 && kind != 1) || tree_height == 0 || tree_height > 64) return B200ZK_ERR_BAD_ARG;
     b200zk_r1cs* r = new b200zk_r1cs();
     r->cs = host::synthesize_update_note(kind, tree_height);
+    *out = r;
+    return B200ZK_OK;
+}
+
+int b200zk_update_account_r1cs(int kind, b200zk_r1cs** out) {
+    if (!out || (kind != 0 && kind != 1)) return B200ZK_ERR_BAD_ARG;
+    b200zk_r1cs* r = new b200zk_r1cs();
+    r->cs = host::synthesize_update_account(kind);
     *out = r;
     return B200ZK_OK;
 }
@@ -340,19 +406,33 @@ int b200zk_poseidon_hash_batch(b200zk_ctx* ctx, const uint8_t* inputs, size_t n_
     return B200ZK_OK;
 }
 
+static int witness_batch_impl(b200zk_ctx* ctx, const b200zk_r1cs* r, int relation, const uint8_t* inputs, size_t batch,
+                              uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status);
+
 int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
                                      uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status) {
+    return witness_batch_impl(ctx, r, host::RELATION_UPDATE_NOTE, inputs, batch, out_assignments, d_out_assignments, out_status);
+}
+
+int b200zk_update_account_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, const uint8_t* inputs, size_t batch,
+                                        uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status) {
+    return witness_batch_impl(ctx, r, host::RELATION_UPDATE_ACCOUNT, inputs, batch, out_assignments, d_out_assignments, out_status);
+}
+
+static int witness_batch_impl(b200zk_ctx* ctx, const b200zk_r1cs* r, int relation, const uint8_t* inputs, size_t batch,
+                              uint8_t* out_assignments, void* d_out_assignments, uint8_t* out_status) {
     if (!ctx || !r || !inputs) return B200ZK_ERR_BAD_ARG;
+    if (r->cs.relation != relation) return fail(ctx, B200ZK_ERR_BAD_ARG, "the R1CS handle belongs to the other relation");
     if (batch == 0) return B200ZK_OK;
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t H = r->cs.tree_height, nv = r->cs.num_variables();
-    const size_t in_bytes = batch * (18 + 2 * (size_t)H) * 32, z_bytes = batch * (size_t)nv * 32;
+    const size_t in_bytes = batch * (size_t)r->cs.inputs_per_instance * 32, z_bytes = batch * (size_t)nv * 32;
     void *din, *dz = d_out_assignments, *dst;
     B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
     if (!dz) B200ZK_TRY(scratch(ctx, "wit_z", z_bytes, &dz));
     B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    B200ZK_TRY(update_note_witness_device(ctx, r->cs.kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
+    B200ZK_TRY(relation_witness_device(ctx, relation, r->cs.kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
     std::vector<uint32_t> st(batch);
     B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_assignments)
@@ -364,7 +444,7 @@ int b200zk_update_note_witness_batch(b200zk_ctx* ctx, const b200zk_r1cs* r, cons
         if (st[i] & 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "witness layout does not match the R1CS (internal error)");
         if (st[i] & 1) rc = B200ZK_ERR_UNSATISFIED;
     }
-    if (rc != B200ZK_OK) fail(ctx, rc, "a witness does not satisfy the update-note relation (see out_status)");
+    if (rc != B200ZK_OK) fail(ctx, rc, "a witness does not satisfy the relation (see out_status)");
     return rc;
 }
 

@@ -34,6 +34,8 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
 int poseidon_consts_device(b200zk_ctx* ctx, const host::PoseidonConsts** out);
 int update_note_witness_device(b200zk_ctx* ctx, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs, size_t batch,
                                Fr* d_z, uint32_t* d_status);
+int relation_witness_device(b200zk_ctx* ctx, int relation, int kind, uint32_t H, uint32_t num_vars, const Fr* d_inputs,
+                            size_t batch, Fr* d_z, uint32_t* d_status);
 
 // verify.cu: zcash / ark-serialize compressed encoding, one thread per point (device buffers)
 int points_compress_device(b200zk_ctx* ctx, int group, const void* d_affine, size_t n, uint8_t* d_out);

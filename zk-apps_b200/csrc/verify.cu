@@ -276,6 +276,36 @@ __global__ void __launch_bounds__(64) points_decompress_kernel(const uint8_t* __
     status[i] = st;
 }
 
+// affine points as an MSM would take them: coordinates reduced, on the curve, in the order-r subgroup
+template <class F>
+__global__ void __launch_bounds__(64) points_validate_kernel(const Affine<F>* __restrict__ in, size_t n, int check_subgroup,
+                                                             int32_t* __restrict__ status) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine<F> p = in[i];
+    int st = POINT_OK;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&p);
+    for (int k = 0; k < (int)(sizeof(Affine<F>) / sizeof(Fq)); k++) {  // every Fq word < p
+        bool lt = false;
+        for (int j = 11; j >= 0; j--) {
+            const uint32_t a = w[k * 12 + j], m = FqCfg::mod(j);
+            if (a != m) {
+                lt = a < m;
+                break;
+            }
+        }
+        if (!lt) st = POINT_BAD_ENCODING;
+    }
+    if (st == POINT_OK) {
+        bool on;
+        if constexpr (sizeof(F) == sizeof(Fq)) on = ec_on_curve(p, g1_b());
+        else on = ec_on_curve(p, g2_b());
+        if (!on) st = POINT_NOT_ON_CURVE;
+        else if (check_subgroup && !ec_in_subgroup(p)) st = POINT_NOT_IN_SUBGROUP;
+    }
+    status[i] = st;
+}
+
 void free_vk(b200zk_vk* vk) {
     if (!vk) return;
     if (vk->d_vk) cudaFree(vk->d_vk);
@@ -527,6 +557,26 @@ int b200zk_points_decompress(b200zk_ctx* ctx, int group, const uint8_t* in, size
     B200ZK_CUDA(ctx, cudaMemcpyAsync(din, in, n * w, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_TRY(points_decompress_device(ctx, group, (const uint8_t*)din, n, check_subgroup != 0, dout, (int32_t*)dst));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(out_affine, dout, n * 2 * w, cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(status, dst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200ZK_OK;
+}
+
+int b200zk_points_validate(b200zk_ctx* ctx, int group, const uint8_t* affine, size_t n, int check_subgroup,
+                           int32_t* status) {
+    if (!ctx || (group != 1 && group != 2) || (n && (!affine || !status))) return B200ZK_ERR_BAD_ARG;
+    if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pt = group == 1 ? sizeof(Affine<Fq>) : sizeof(Affine<Fq2>);
+    void *din, *dst;
+    B200ZK_TRY(scratch(ctx, "wire_out", n * pt, &din));
+    B200ZK_TRY(scratch(ctx, "wire_status", n * sizeof(int32_t), &dst));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(din, affine, n * pt, cudaMemcpyHostToDevice, ctx->stream));
+    if (group == 1)
+        points_validate_kernel<Fq><<<div_up(n, 64), 64, 0, ctx->stream>>>((const Affine<Fq>*)din, n, check_subgroup, (int32_t*)dst);
+    else
+        points_validate_kernel<Fq2><<<div_up(n, 64), 64, 0, ctx->stream>>>((const Affine<Fq2>*)din, n, check_subgroup, (int32_t*)dst);
+    B200ZK_TRY(check_launch(ctx, "points_validate"));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(status, dst, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;

@@ -20,7 +20,7 @@ _FR_RINV = pow(_FR_R, -1, R_MOD)
 
 STATUS = {0: "OK", -1: "BAD_ARG", -2: "BAD_LEN", -3: "DOMAIN_TOO_LARGE", -4: "CUDA", -5: "NO_DEVICE",
           -6: "UNSATISFIED", -7: "NOT_IMPLEMENTED", -8: "MERKLE_LIMIT_EXCEEDED", -9: "MERKLE_PROOF_GEN_FAIL",
-          -10: "MERKLE_NON_EXISTING_NODE"}
+          -10: "MERKLE_NON_EXISTING_NODE", -11: "BAD_ENCODING", -12: "NCCL"}
 
 
 class B200zkError(RuntimeError):
@@ -82,6 +82,9 @@ def lib() -> C.CDLL:
             "b200zk_points_sum": (i32, [vp, i32, vp, sz, vp, vp]),
             "b200zk_points_sum_device": (i32, [vp, i32, vp, sz, vp]),
             "b200zk_update_note_r1cs": (i32, [i32, u32, C.POINTER(vp)]),
+            "b200zk_update_account_r1cs": (i32, [i32, C.POINTER(vp)]),
+            "b200zk_update_account_witness_batch": (i32, [vp, vp, vp, sz, vp, vp, vp]),
+            "b200zk_update_account_prove_batch": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
             "b200zk_r1cs_free": (None, [vp]),
             "b200zk_r1cs_shape": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64 * 3)]),
@@ -117,6 +120,16 @@ def lib() -> C.CDLL:
             "b200zk_vk_deserialize": (i32, [vp, vp, sz, i32, C.POINTER(vp)]),
             "b200zk_pk_serialize": (i32, [vp, vp, vp, vp, C.POINTER(sz)]),
             "b200zk_pk_deserialize": (i32, [vp, vp, vp, sz, i32, i32, C.POINTER(vp), C.POINTER(vp)]),
+            "b200zk_points_validate": (i32, [vp, i32, vp, sz, i32, vp]),
+            "b200zk_init_multi": (i32, [i32, C.POINTER(vp)]),
+            "b200zk_comm_unique_id": (i32, [vp]),
+            "b200zk_comm_init": (i32, [vp, vp, i32, i32]),
+            "b200zk_comm_destroy": (i32, [vp]),
+            "b200zk_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+            "b200zk_msm_sharded": (i32, [vp, vp, vp, i32, sz, vp, vp]),
+            "b200zk_msm_sharded_device": (i32, [vp, vp, vp, i32, sz, vp]),
+            "b200zk_msm_sharded_multi": (i32, [C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp), i32, C.POINTER(sz), vp, vp]),
+            "b200zk_ntt_sharded_device": (i32, [vp, vp, u32, u32, i32]),
             "b200zk_stat_get": (i32, [vp, C.c_char_p, C.POINTER(C.c_double)]),
             "b200zk_stat_reset": (i32, [vp]),
         }
@@ -179,6 +192,72 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self.check(lib().b200zk_set_option(self._h, name.encode(), int(value)))
+
+    # ---- communicator (NCCL behind the C ABI, csrc/comm.cu)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """The 128-byte ncclUniqueId rank 0 hands to the other ranks."""
+        buf = C.create_string_buffer(128)
+        rc = lib().b200zk_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise B200zkError(rc, "b200zk_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, uid: bytes | None, rank: int, world: int):
+        """Collective over all ranks of the job."""
+        p, keep = _buf(uid) if uid is not None else (None, None)
+        self.check(lib().b200zk_comm_init(self._h, p, rank, world))
+
+    def comm_init_from_dist(self, dist=None):
+        """Bootstrap through an existing torch.distributed process group (any backend): rank 0 creates the id and
+        broadcasts it as an object.  world size 1 needs neither NCCL nor a process group."""
+        if dist is None:
+            self.comm_init(None, 0, 1)
+            return
+        box = [self.comm_unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], dist.get_rank(), dist.get_world_size())
+
+    def comm_info(self):
+        r, w = C.c_int(), C.c_int()
+        self.check(lib().b200zk_comm_info(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def comm_destroy(self):
+        self.check(lib().b200zk_comm_destroy(self._h))
+
+    def msm_sharded(self, bases_local, scalars=None, n: int | None = None, device_ptr: int | None = None):
+        """VariableBaseMSM over the communicator: this rank's slice of bases / scalars -> (affine bytes, is_inf),
+        the same on every rank."""
+        pt = G1_BYTES if bases_local.group == 1 else G2_BYTES
+        out = np.zeros(pt, dtype=np.uint8)
+        inf = C.c_uint8()
+        if device_ptr is not None:
+            ps, on_dev = C.c_void_p(device_ptr), 1
+        else:
+            ps, ks = _buf(scalars)
+            on_dev = 0
+            if n is None:
+                n = ks.nbytes // 32 if ks is not None else 0
+        self.check(lib().b200zk_msm_sharded(self._h, bases_local._h, ps, on_dev, n, out.ctypes.data_as(C.c_void_p),
+                                            C.byref(inf)))
+        return out.tobytes(), bool(inf.value)
+
+    def msm_sharded_device(self, bases_local, d_scalars: int, n: int, d_out: int):
+        """Same, result left in device memory, nothing synchronised (one stream of work)."""
+        self.check(lib().b200zk_msm_sharded_device(self._h, bases_local._h, C.c_void_p(d_scalars), 1, n, C.c_void_p(d_out)))
+
+    def ntt_sharded_device(self, d_local: int, log_n: int, log_n1: int, inverse: bool = False):
+        """Four-step NTT over the communicator, in place on this rank's n / world elements: layout L(n1, n2) in,
+        L(n2, n1) out (include/b200zk.h)."""
+        self.check(lib().b200zk_ntt_sharded_device(self._h, C.c_void_p(d_local), log_n, log_n1, 1 if inverse else 0))
+
+    def points_validate(self, group: int, points, check_subgroup: bool = True) -> np.ndarray:
+        pp, kp = _buf(points)
+        n = kp.nbytes // (G1_BYTES if group == 1 else G2_BYTES)
+        st = np.zeros(n, dtype=np.int32)
+        self.check(lib().b200zk_points_validate(self._h, group, pp, n, 1 if check_subgroup else 0, st.ctypes.data_as(C.c_void_p)))
+        return st
 
     # ---- device memory
     def alloc(self, nbytes: int) -> int:
@@ -414,19 +493,27 @@ class UpdateNoteRelation:
     """The R1CS of update_note_circuit (shielder/relations/src/relations/update_note.rs:106-149):
     the ConstraintSynthesizer of this backend.  Host-only; needs no GPU."""
 
+    _witness_fn = "b200zk_update_note_witness_batch"
+
     def __init__(self, kind: int = WITHDRAW, tree_height: int = 10):
         self.kind, self.tree_height = kind, tree_height
         self._h = C.c_void_p()
-        rc = lib().b200zk_update_note_r1cs(kind, tree_height, C.byref(self._h))
+        rc = self._make(kind, tree_height)
         if rc != 0:
-            raise B200zkError(rc, "b200zk_update_note_r1cs")
+            raise B200zkError(rc, "r1cs synthesis")
+        self._shape()
+
+    def _make(self, kind, tree_height):
+        self.n_inputs_per_proof = 18 + 2 * tree_height
+        return lib().b200zk_update_note_r1cs(kind, tree_height, C.byref(self._h))
+
+    def _shape(self):
         nc, ni, na = C.c_uint64(), C.c_uint64(), C.c_uint64()
         nnz = (C.c_uint64 * 3)()
         lib().b200zk_r1cs_shape(self._h, C.byref(nc), C.byref(ni), C.byref(na), C.byref(nnz))
         self.num_constraints, self.num_inputs, self.num_aux = nc.value, ni.value, na.value
         self.num_variables = ni.value + na.value
         self.nnz = list(nnz)
-        self.n_inputs_per_proof = 18 + 2 * tree_height
 
     @property
     def handle(self):
@@ -448,7 +535,10 @@ class UpdateNoteRelation:
         pi, ki = _buf(inputs)
         out = np.zeros(batch * self.num_variables * 32, dtype=np.uint8) if want_host else None
         status = np.zeros(batch, dtype=np.uint8)
-        rc = lib().b200zk_update_note_witness_batch(
+        if ki.nbytes != batch * self.n_inputs_per_proof * 32:
+            raise ValueError("inputs: expected %d bytes (batch x %d x 32), got %d" % (batch * self.n_inputs_per_proof * 32,
+                                                                                     self.n_inputs_per_proof, ki.nbytes))
+        rc = getattr(lib(), self._witness_fn)(
             ctx.handle, self._h, pi, batch, out.ctypes.data_as(C.c_void_p) if want_host else None,
             C.c_void_p(device_out) if device_out else None, status.ctypes.data_as(C.c_void_p))
         if rc not in (0, -6):
@@ -461,6 +551,20 @@ class UpdateNoteRelation:
             self._h = None
 
     __del__ = free
+
+
+class UpdateAccountRelation(UpdateNoteRelation):
+    """The R1CS of update_account_circuit as a relation of its own (relations/src/relations/update_account.rs:68-95):
+    instance (old_account_hash, new_account_hash, amount, token, user), witness old_account; rows of 9 Fr."""
+
+    _witness_fn = "b200zk_update_account_witness_batch"
+
+    def __init__(self, kind: int = WITHDRAW):
+        super().__init__(kind, 0)
+
+    def _make(self, kind, tree_height):
+        self.n_inputs_per_proof = 9
+        return lib().b200zk_update_account_r1cs(kind, C.byref(self._h))
 
 
 def poseidon_hash_batch(ctx: Context, inputs, arity: int) -> np.ndarray:
@@ -676,6 +780,16 @@ class Groth16:
     """ark_groth16::Groth16::<Bls12_381> call sites (names per arkworks 0.4 [recall])."""
 
     @staticmethod
+    def _check_verify_buffers(vk: "VerifyingKey", kp: np.ndarray, ki: np.ndarray, batch: int):
+        """The C side reads batch*192 proof bytes and batch*(num_inputs-1)*32 input bytes: a short host buffer
+        would be an out-of-bounds read, so sizes are checked here."""
+        if kp.size != batch * 192:
+            raise ValueError("proofs: expected %d bytes (batch x 192), got %d" % (batch * 192, kp.size))
+        want = batch * (vk.num_inputs - 1) * 32
+        if ki.size != want:
+            raise ValueError("public_inputs: expected %d bytes (batch x (num_inputs - 1) x 32), got %d" % (want, ki.size))
+
+    @staticmethod
     def verify_proofs(vk: VerifyingKey, proofs, public_inputs, batch: int | None = None, check_subgroup: bool = True,
                       device: bool = False) -> np.ndarray:
         """Groth16::verify_proof for a batch: proofs = batch x 192 B compressed, public_inputs = batch x
@@ -689,6 +803,7 @@ class Groth16:
             pi, ki = _buf(public_inputs)
             if batch is None:
                 batch = kp.size // 192
+            Groth16._check_verify_buffers(vk, kp, ki, batch)
         st = np.zeros(batch, dtype=np.int32)
         ctx.check(lib().b200zk_groth16_verify_batch(ctx.handle, vk._h, pp, pi, 1 if device else 0, batch,
                                                     1 if check_subgroup else 0, st.ctypes.data_as(C.c_void_p)))
@@ -707,7 +822,10 @@ class Groth16:
             pi, ki = _buf(public_inputs)
             if batch is None:
                 batch = kp.size // 192
+            Groth16._check_verify_buffers(vk, kp, ki, batch)
         pc, kc = _buf(coeffs)
+        if kc.size != batch * 16:
+            raise ValueError("coeffs: expected %d bytes (batch x 16), got %d" % (batch * 16, kc.size))
         ok = C.c_int()
         ctx.check(lib().b200zk_groth16_verify_aggregate(ctx.handle, vk._h, pp, pi, 1 if device else 0, batch, pc,
                                                         1 if check_subgroup else 0, C.byref(ok)))
@@ -767,6 +885,15 @@ class Groth16:
         return proofs
 
     @staticmethod
+    def create_random_proof(pk: ProvingKey, inputs, rng):
+        """ark_groth16 `create_random_proof_with_reduction(circuit, &pk, rng)`: draws r, THEN s from `rng` (an object
+        with .fr() -> int in [0, r), the stand-in for `Fr::rand(rng)`) and proves one instance."""
+        r = rng.fr()
+        s = rng.fr()
+        proofs, status = Groth16.prove_update_note(pk, inputs, [r], [s], 1)
+        return proofs
+
+    @staticmethod
     def prove_update_note(pk: ProvingKey, inputs, r, s, batch: int):
         """Witness generation (K6) + proving in one call: the user-facing path.  r, s: uint8 arrays
         (batch x 32 B canonical) or lists of ints."""
@@ -779,8 +906,11 @@ class Groth16:
         pi, ki = _buf(inputs)
         proofs = np.zeros(batch * 192, dtype=np.uint8)
         status = np.zeros(batch, dtype=np.uint8)
-        rc = lib().b200zk_update_note_prove_batch(ctx.handle, pk._h, pi, batch, rb.ctypes.data_as(C.c_void_p),
-                                                  sb.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
-                                                  status.ctypes.data_as(C.c_void_p))
+        fn = (lib().b200zk_update_account_prove_batch if isinstance(pk.relation, UpdateAccountRelation)
+              else lib().b200zk_update_note_prove_batch)
+        if ki.nbytes != batch * pk.relation.n_inputs_per_proof * 32 or rb.nbytes != batch * 32 or sb.nbytes != batch * 32:
+            raise ValueError("inputs / r / s do not match the batch size")
+        rc = fn(ctx.handle, pk._h, pi, batch, rb.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p),
+                proofs.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p))
         ctx.check(rc)
         return proofs, status

@@ -1,23 +1,27 @@
-"""Multi-GPU host side: one process per GPU, `torch.distributed` for the plumbing.
+"""Multi-GPU host side: one process per GPU.
+
+The product path is the C ABI (csrc/comm.cu): `b200zk_comm_init` attaches an NCCL communicator to the ctx and
+`b200zk_msm_sharded[_device]` / `b200zk_ntt_sharded_device` run local kernels, collective and combine step as one
+stream of work inside libb200zk.so -- no torch on the data path, no host synchronisation between the steps.  With
+the GPU backend the classes below are thin callers of those entry points; `torch.distributed` is only the
+bootstrap that carries the 128-byte NCCL id from rank 0 to the others.
 
 * ShardedMSM      -- a large MSM split by contiguous point range.  Every rank runs the full bucket
-                     pipeline on its slice (b200zk_msm_resident_device leaves the affine partial in this
-                     rank's slot of the all_gather buffer, in device memory); one all_gather of
-                     world * 96 B (G1) / 192 B (G2) follows and every rank adds the partials
-                     (b200zk_points_sum_device) -- curve addition is not an NCCL reduction op.
+                     pipeline on its slice; the last kernel leaves the affine partial in this rank's slot of
+                     the all_gather buffer; one in-place all_gather of world * 96 B (G1) / 192 B (G2) follows and
+                     every rank adds the partials -- curve addition is not an NCCL reduction op.
 * ShardedNTT      -- a large Fr NTT as a four-step transform with ONE exchange: n = n1 * n2, rank g owns
                      the columns j2 in [g*C, (g+1)*C) (C = n2 / G) as local[c][j1] = x[j1*n2 + g*C + c].
                      Local column transforms -> twiddle w_n^(j2*k1) fused into a transpose that leaves the
-                     data chunk-major by destination (b200zk_ntt_twiddle_transpose_device) -> all_to_all
-                     of (n1/G) x C chunks -> rows interleaved -> local row transforms.  The output has the
-                     same kind of layout with n1 and n2 swapped (rank h: out[r][k2] = X[(h*R + r) + n1*k2]),
-                     so an inverse transform consumes it directly.
+                     data chunk-major by destination -> all_to_all of (n1/G) x C chunks -> rows interleaved ->
+                     local row transforms.  The output has the same kind of layout with n1 and n2 swapped
+                     (rank h: out[r][k2] = X[(h*R + r) + n1*k2]), so an inverse transform consumes it directly.
 * ProofSharder    -- independent proofs of a batch spread round-robin over the ranks; no collective on
                      the data path, only a gather of the 192-byte proofs to rank 0.
 
-The arithmetic is delegated to a `backend`, so the partition / exchange logic runs unchanged with the
-gloo backend on CPU in the tests (tests/test_sharded_cpu.py plugs the oracle in as the backend; the
-product backend below is the only one this package ships and it needs the GPU library).
+The same partition / exchange steps are also spelled out here over a pluggable `backend`, so that they run with the
+gloo backend on CPU in the tests (tests/test_sharded_cpu.py plugs the oracle in as the arithmetic): that generic
+path is the executable description of what comm.cu does, not a second product path -- GpuBackend never takes it.
 """
 from __future__ import annotations
 
@@ -48,61 +52,19 @@ class _Dist:
 
 
 class GpuBackend:
-    """Product backend: libb200zk on this rank's GPU."""
+    """Product backend: libb200zk on this rank's GPU, communicator inside the library (csrc/comm.cu)."""
 
-    def __init__(self, ctx):
+    native = True     # ShardedMSM / ShardedNTT call the C ABI's sharded entry points directly
+
+    def __init__(self, ctx, dist=None):
         import torch
         self.ctx, self.torch = ctx, torch
         self.device = torch.device("cuda", torch.cuda.current_device())
+        if ctx.comm_info()[1] == 1 and dist is not None and dist.get_world_size() > 1:
+            ctx.comm_init_from_dist(dist)
 
-    def gather_buffer(self, nbytes: int):
-        return self.torch.zeros(nbytes, dtype=self.torch.uint8, device=self.device)
-
-    def msm_into(self, bases, scalars, n, buf, offset):
-        bases.msm_to_device(buf.data_ptr() + offset, scalars=scalars if not isinstance(scalars, int) else None,
-                            device_ptr=scalars if isinstance(scalars, int) else None, n=n)
-        self.ctx.sync()                                   # the collective runs on torch's stream
-
-    def sum_points(self, group, buf, count):
-        from .ffi import lib
-        import ctypes as C
-        pt = G1_BYTES if group == 1 else G2_BYTES
-        out = self.torch.zeros(pt, dtype=self.torch.uint8, device=self.device)
-        self.torch.cuda.current_stream().synchronize()    # all_gather done before our stream reads the buffer
-        self.ctx.check(lib().b200zk_points_sum_device(self.ctx.handle, group, C.c_void_p(buf.data_ptr()), count,
-                                                      C.c_void_p(out.data_ptr())))
-        self.ctx.sync()
-        return out.cpu().numpy().tobytes()
-
-
-    # ---- ShardedNTT primitives: buffers are torch uint8 tensors on this rank's GPU
     def buffer(self, nbytes: int):
         return self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
-
-    def ntt_batch(self, buf, log_len: int, inverse: bool, batch: int):
-        from .ffi import lib
-        import ctypes as C
-        self.ctx.check(lib().b200zk_ntt_fr_device(self.ctx.handle, C.c_void_p(buf.data_ptr()), log_len,
-                                                  1 if inverse else 0, None, batch))
-
-    def twiddle_transpose(self, src, dst, log_n: int, rows: int, cols: int, row0: int, inverse: bool):
-        from .ffi import lib
-        import ctypes as C
-        self.ctx.check(lib().b200zk_ntt_twiddle_transpose_device(self.ctx.handle, C.c_void_p(src.data_ptr()),
-                                                                 C.c_void_p(dst.data_ptr()), log_n, rows, cols, row0,
-                                                                 1 if inverse else 0))
-
-    def copy2d(self, dst, dst_off: int, dpitch: int, src, src_off: int, spitch: int, width: int, height: int):
-        from .ffi import lib
-        import ctypes as C
-        self.ctx.check(lib().b200zk_copy2d_device(self.ctx.handle, C.c_void_p(dst.data_ptr() + dst_off), dpitch,
-                                                  C.c_void_p(src.data_ptr() + src_off), spitch, width, height))
-
-    def before_collective(self):
-        self.ctx.sync()                                   # our stream -> torch's (NCCL) stream
-
-    def after_collective(self):
-        self.torch.cuda.current_stream().synchronize()    # NCCL done before our stream touches the buffer
 
 
 class ShardedMSM:
@@ -115,12 +77,18 @@ class ShardedMSM:
         self.d = _Dist(dist)
         self.lo, self.hi = shard_range(n_total, self.d.rank, self.d.world)
         self.pt = G1_BYTES if group == 1 else G2_BYTES
-        self.buf = backend.gather_buffer(self.d.world * self.pt)
+        self.native = getattr(backend, "native", False)
+        if not self.native:
+            self.buf = backend.gather_buffer(self.d.world * self.pt)
 
     def msm(self, scalars_local) -> bytes:
         """scalars_local: this rank's (hi - lo) canonical scalars (host uint8 array, or a device address).
         Returns the affine result, identical on every rank."""
         n = self.hi - self.lo
+        if self.native:      # b200zk_msm_sharded: local pipeline -> in-place all_gather -> sum, one stream
+            if isinstance(scalars_local, int):
+                return self.backend.ctx.msm_sharded(self.bases, device_ptr=scalars_local, n=n)[0]
+            return self.backend.ctx.msm_sharded(self.bases, scalars=scalars_local, n=n)[0]
         self.backend.msm_into(self.bases, scalars_local, n, self.buf, self.d.rank * self.pt)
         if self.d.world > 1:
             mine = self.buf[self.d.rank * self.pt:(self.d.rank + 1) * self.pt]
@@ -168,13 +136,18 @@ class ShardedNTT:
         self.C = (1 << self.log_n2) // w          # columns this rank owns
         self.R = (1 << self.log_n1) // w          # rows this rank owns after the exchange
         nbytes = self.C * (1 << self.log_n1) * 32
-        self.send = backend.buffer(nbytes)
-        self.recv = backend.buffer(nbytes) if w > 1 else None
+        self.native = getattr(backend, "native", False)
+        if not self.native:
+            self.send = backend.buffer(nbytes)
+            self.recv = backend.buffer(nbytes) if w > 1 else None
 
     def swapped(self) -> "ShardedNTT":
         return ShardedNTT(self.backend, self.log_n, self.d.dist, self.log_n2)
 
     def _run(self, local, inverse: bool):
+        if self.native:      # b200zk_ntt_sharded_device: asynchronous on the ctx stream, in place
+            self.backend.ctx.ntt_sharded_device(local.data_ptr(), self.log_n, self.log_n1, inverse)
+            return local
         b, w, g = self.backend, self.d.world, self.d.rank
         n1, n2 = 1 << self.log_n1, 1 << self.log_n2
         b.ntt_batch(local, self.log_n1, inverse, self.C)                               # columns, in place
@@ -183,9 +156,7 @@ class ShardedNTT:
             out = local                                                                  # send is [n1][n2] already
             b.copy2d(out, 0, n2 * 32, self.send, 0, n2 * 32, n2 * 32, n1)
         else:
-            b.before_collective()
             self.d.dist.all_to_all_single(self.recv, self.send)                          # recv[g'][r][c]
-            b.after_collective()
             out = local                                                                  # R x n2, same byte count
             chunk = self.R * self.C * 32
             for src in range(w):                                                         # out[r][src*C + c]
