@@ -327,6 +327,23 @@ int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const u
 /* witness generation + proving for a key made from b200zk_update_account_r1cs (rows of 9 Fr, see above) */
 int b200zk_update_account_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
                                       const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status);
+/* Asynchronous form: up to TWO batches in flight per ctx.  _submit stages the host buffers (inputs unless
+ * inputs_on_device, r, s) in pinned memory of the library, enqueues witness generation and proving, and returns a
+ * ticket without waiting for the GPU: the caller's input buffers are free again on return.  b200zk_prove_wait(ticket)
+ * blocks until that batch is done and THEN fills proofs_out (batch * 192 B) and out_status (may be NULL) given to
+ * _submit -- those two must stay valid until the wait; this is the one place where the library keeps host pointers
+ * across calls.  An unsatisfied witness is reported by the wait (B200ZK_ERR_UNSATISFIED, nothing written to
+ * proofs_out).  Submitting batch k+1 before waiting for batch k lets the head of one batch (input copy, witness
+ * generation, sorting) and the tail of the other (bucket reduction, assembly) run under bucket accumulation: each
+ * batch has its own main stream and scratch buffers, the MSM streams are shared.  The synchronous calls above are
+ * submit + wait.  Tickets must be awaited in the order they were issued before a third submit. */
+int b200zk_update_note_prove_submit(b200zk_ctx* ctx, const b200zk_pk* pk, const void* inputs, int inputs_on_device,
+                                    size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                    uint8_t* out_status, uint64_t* ticket);
+int b200zk_update_account_prove_submit(b200zk_ctx* ctx, const b200zk_pk* pk, const void* inputs, int inputs_on_device,
+                                       size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                       uint8_t* out_status, uint64_t* ticket);
+int b200zk_prove_wait(b200zk_ctx* ctx, uint64_t ticket);
 /* same with the instance inputs already resident in device memory (r, s, proofs stay host buffers) */
 int b200zk_update_note_prove_batch_device(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_inputs, size_t batch,
                                           const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,

@@ -211,9 +211,14 @@ def test_update_account_proofs_bit_exact_and_verify(ctx):
     wrong = ws[0].public_inputs(); wrong[1] = (wrong[1] + 1) % R
     assert not og.verify_with_vk(vk, wrong, og.proof_from_bytes(bytes(proofs[:192])))
     # a key of the other relation is refused, not misused
-    note_rel = z.UpdateNoteRelation(rel.WITHDRAW, 4)
-    with pytest.raises((z.B200zkError, ValueError)):
-        z.Groth16.prove_update_note(z.ProvingKey(ctx, note_rel, pk._h, None), inputs, rs, ss, 3)
+    import ctypes as C
+    out = np.zeros(3 * 192, dtype=np.uint8)
+    rb = np.frombuffer(b"".join(int(x).to_bytes(32, "little") for x in rs), dtype=np.uint8)
+    note_rows = np.zeros(3 * (18 + 2 * rel.TREE_HEIGHT) * 32, dtype=np.uint8)
+    rc = z.lib().b200zk_update_note_prove_batch(ctx.handle, pk._h, note_rows.ctypes.data_as(C.c_void_p), 3,
+                                                rb.ctypes.data_as(C.c_void_p), rb.ctypes.data_as(C.c_void_p),
+                                                out.ctypes.data_as(C.c_void_p), None)
+    assert rc == -1                                                 # B200ZK_ERR_BAD_ARG: the key is update-account's
     pk.free()
 
 
@@ -259,3 +264,42 @@ def test_create_random_proof_draws_r_then_s(ctx, withdraw_key):
     zz = rel.synthesize_update_note(w).z
     assert bytes(proof) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, zz, rng.drawn[0], rng.drawn[1]))   # r first, s second
     assert og.verify_with_vk(og.verifying_key_from_toxic(sc, TOX), w.public_inputs(), og.proof_from_bytes(bytes(proof)))
+
+
+def test_async_submit_wait_matches_the_synchronous_call(ctx, withdraw_key):
+    """b200zk_update_note_prove_submit / b200zk_prove_wait: two batches in flight give the same proof bytes as the
+    synchronous call; the caller's input buffer may be reused right after submit; a third submit without a wait and
+    a wait on an unknown ticket are refused; an unsatisfied instance surfaces at the wait."""
+    relation, pk, M, sc = withdraw_key
+    B = 5
+    sets, want = [], []
+    rs = util.scalars_array(util.rand_fr(31, B)); ss = util.scalars_array(util.rand_fr(32, B))
+    for k in range(3):
+        ws = [rel.make_witness(200 + 10 * k + i, rel.WITHDRAW) for i in range(B)]
+        inp = util.fr_mont_array([v for w in ws for v in rel.witness_to_inputs(w)])
+        sets.append(inp)
+        want.append(bytes(z.Groth16.prove_update_note(pk, inp, rs, ss, B)[0]))
+    outs = [np.zeros(B * 192, dtype=np.uint8) for _ in range(3)]
+    sts = [np.full(B, 9, dtype=np.uint8) for _ in range(3)]
+    scratch_in = sets[0].copy()
+    t0 = z.Groth16.prove_submit(pk, scratch_in, rs, ss, B, outs[0], sts[0])
+    scratch_in[:] = sets[1]                                            # the input buffer is free again after submit
+    t1 = z.Groth16.prove_submit(pk, scratch_in, rs, ss, B, outs[1], sts[1])
+    with pytest.raises(z.B200zkError):
+        z.Groth16.prove_submit(pk, sets[2], rs, ss, B, outs[2], sts[2])     # two already in flight
+    with pytest.raises(z.B200zkError):
+        z.Groth16.prove_wait(pk, t1 + 100)
+    z.Groth16.prove_wait(pk, t0)
+    t2 = z.Groth16.prove_submit(pk, sets[2], rs, ss, B, outs[2], sts[2])
+    z.Groth16.prove_wait(pk, t1)
+    z.Groth16.prove_wait(pk, t2)
+    for k in range(3):
+        assert bytes(outs[k]) == want[k] and list(sts[k]) == [0] * B
+    bad = sets[0].copy(); bad[4 * 32] ^= 1                             # merkle_root of instance 0
+    out = np.zeros(B * 192, dtype=np.uint8); st = np.zeros(B, dtype=np.uint8)
+    t = z.Groth16.prove_submit(pk, bad, rs, ss, B, out, st)
+    with pytest.raises(z.B200zkError) as e:
+        z.Groth16.prove_wait(pk, t)
+    assert e.value.code == -6 and list(st) == [1, 0, 0, 0, 0] and not out.any()
+    # the ctx is usable afterwards, synchronous calls included
+    assert bytes(z.Groth16.prove_update_note(pk, sets[1], rs, ss, B)[0]) == want[1]

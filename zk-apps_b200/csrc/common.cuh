@@ -29,12 +29,21 @@ struct DeviceBuf {
 struct b200zk_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;                         // main stream (slot 0)
-    static constexpr int AUX_STREAMS = 4;                  // slots 1..4: independent MSMs of one proof batch
-    cudaStream_t aux[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;                         // main stream (slot 0) of the ACTIVE lane, = main_lane[lane]
+    // Two proof batches can be in flight (b200zk_*_prove_submit / b200zk_prove_wait): each has its own main stream
+    // (witness -> H(x) -> assembly) and its own copy of every slot-0 scratch buffer ("lane"), while the MSM streams
+    // below are shared, so the five MSMs of batch k+1 queue behind those of batch k and the head of one batch and
+    // the tail of the other hide under bucket accumulation.
+    static constexpr int LANES = 2;
+    cudaStream_t main_lane[LANES] = {nullptr, nullptr};
+    int lane = 0;
+    cudaEvent_t lane_done[LANES] = {nullptr, nullptr};     // everything of the batch submitted on that lane has finished
+    static constexpr int AUX_STREAMS = 5;                  // slots 1..5: the independent MSMs of a proof batch (a, b_g1, l, b_g2, h)
+    cudaStream_t aux[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[AUX_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t fin = nullptr, fin2 = nullptr;            // high priority: latency-bound proof assembly pieces
     cudaEvent_t ev_fin2 = nullptr, ev_fork2 = nullptr;     // fin2 joined into main; fin_scalars done
+    cudaEvent_t ev_h = nullptr;                            // H(x) coefficients ready: the h MSM may start
     cudaEvent_t ev_msm[3] = {nullptr, nullptr, nullptr};   // completion of the a / b_g1 / b_g2 MSMs
     bool concurrency = true;                               // b200zk_set_option("concurrency")
     int msm_parts = 0;                                     // b200zk_set_option("msm_parts"): 0 = automatic
@@ -54,6 +63,18 @@ struct b200zk_ctx {
     long launches = 0;                                     // every kernel launch of this library
     std::map<std::string, double> stats;                   // work counters (b200zk_stat_get)
     void* poseidon_consts = nullptr;                       // device copy, see poseidon.cu
+    struct PendingBatch {                                  // a submitted, not yet awaited proof batch (one per lane)
+        bool active = false;
+        uint64_t ticket = 0;
+        size_t batch = 0;
+        uint8_t* proofs_out = nullptr;                     // caller's buffers, filled at wait time
+        uint8_t* status_out = nullptr;
+        uint8_t* h_proofs = nullptr;                       // pinned staging (grow-only)
+        uint32_t* h_status = nullptr;
+        uint8_t* h_in = nullptr;                           // pinned staging of inputs | r | s
+        size_t h_proofs_cap = 0, h_status_cap = 0, h_in_cap = 0;
+    } pending[LANES];
+    uint64_t next_ticket = 1;
     void* nccl_comm = nullptr;                             // ncclComm_t of this rank (csrc/comm.cu), null without one
     int comm_rank = 0, comm_world = 1;
 };
@@ -86,7 +107,10 @@ inline cudaStream_t slot_stream(b200zk_ctx* ctx, int slot) {
 
 // grow-only named scratch allocation (slot > 0: a private copy for work running on an aux stream)
 inline int scratch(b200zk_ctx* ctx, const char* name, size_t bytes, void** out, int slot = 0) {
-    DeviceBuf& b = ctx->scratch[slot > 0 ? std::string(name) + "#" + std::to_string(slot) : std::string(name)];
+    // slot > 0: the buffer belongs to a shared MSM stream (work on it is serialised by the stream);
+    // slot 0: it belongs to the active lane's main stream, so lane 1 gets its own copy
+    DeviceBuf& b = ctx->scratch[slot > 0 ? std::string(name) + "#" + std::to_string(slot)
+                                : ctx->lane ? std::string(name) + "@" + std::to_string(ctx->lane) : std::string(name)];
     if (b.bytes < bytes) {
         if (b.ptr) B200ZK_CUDA(ctx, cudaFree(b.ptr));
         b.ptr = nullptr;
@@ -148,5 +172,10 @@ struct ProfScope {
 };
 
 inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+inline void set_lane(b200zk_ctx* ctx, int lane) {
+    ctx->lane = lane;
+    ctx->stream = ctx->main_lane[lane];
+}
 
 }  // namespace b200zk

@@ -28,12 +28,15 @@ int b200zk_init(int device, b200zk_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     auto prio = [&](int level) { return std::min(prio_lo, prio_hi + level); };
-    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio(1)) != cudaSuccess) {
-        delete ctx;
-        return B200ZK_ERR_CUDA;
-    }
+    for (int l = 0; l < b200zk_ctx::LANES; l++)
+        if (cudaStreamCreateWithPriority(&ctx->main_lane[l], cudaStreamNonBlocking, prio(1)) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->lane_done[l], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return B200ZK_ERR_CUDA;
+        }
+    ctx->stream = ctx->main_lane[0];
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) {
-        static const int level[b200zk_ctx::AUX_STREAMS] = {2, 3, 5, 4};  // slots 1..4 = a, b_g1, l, b_g2
+        static const int level[b200zk_ctx::AUX_STREAMS] = {2, 3, 5, 4, 1};  // slots 1..5 = a, b_g1, l, b_g2, h
         if (cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, prio(level[i])) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
             delete ctx;
@@ -43,7 +46,8 @@ int b200zk_init(int device, b200zk_ctx** out) {
     if (cudaStreamCreateWithPriority(&ctx->fin, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->fin2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fin2, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_h, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return B200ZK_ERR_CUDA;
     }
@@ -93,6 +97,7 @@ void b200zk_destroy(b200zk_ctx* ctx) {
     if (ctx->fin2) cudaStreamDestroy(ctx->fin2);
     if (ctx->ev_fin2) cudaEventDestroy(ctx->ev_fin2);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_h) cudaEventDestroy(ctx->ev_h);
     for (int i = 0; i < 3; i++)
         if (ctx->ev_msm[i]) cudaEventDestroy(ctx->ev_msm[i]);
     for (auto& kv : ctx->scratch)
@@ -105,7 +110,13 @@ void b200zk_destroy(b200zk_ctx* ctx) {
         cudaEventDestroy(std::get<2>(t));
     }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    for (int l = 0; l < b200zk_ctx::LANES; l++) {
+        if (ctx->main_lane[l]) cudaStreamDestroy(ctx->main_lane[l]);
+        if (ctx->lane_done[l]) cudaEventDestroy(ctx->lane_done[l]);
+        if (ctx->pending[l].h_proofs) cudaFreeHost(ctx->pending[l].h_proofs);
+        if (ctx->pending[l].h_status) cudaFreeHost(ctx->pending[l].h_status);
+        if (ctx->pending[l].h_in) cudaFreeHost(ctx->pending[l].h_in);
+    }
     delete ctx;
 }
 
@@ -113,7 +124,7 @@ const char* b200zk_last_error(b200zk_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int b200zk_sync(b200zk_ctx* ctx) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
-    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < b200zk_ctx::LANES; l++) B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->main_lane[l]));
     return B200ZK_OK;
 }
 
@@ -128,7 +139,7 @@ int b200zk_dev_free(b200zk_ctx* ctx, void* dptr) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     // work on any stream of the ctx may still read the buffer (auxiliary MSM streams, assembly streams)
-    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < b200zk_ctx::LANES; l++) B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->main_lane[l]));
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->aux[i]));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->fin));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->fin2));
@@ -153,7 +164,7 @@ int b200zk_dev_download(b200zk_ctx* ctx, void* host, const void* dptr, size_t by
 void* b200zk_stream(b200zk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 static void prof_resolve(b200zk_ctx* ctx) {
-    cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < b200zk_ctx::LANES; l++) cudaStreamSynchronize(ctx->main_lane[l]);
     for (int i = 0; i < b200zk_ctx::AUX_STREAMS; i++) cudaStreamSynchronize(ctx->aux[i]);
     if (ctx->fin) cudaStreamSynchronize(ctx->fin);
     if (ctx->fin2) cudaStreamSynchronize(ctx->fin2);

@@ -135,17 +135,17 @@ HD void ec_madd(XYZZ<F>& acc, const Affine<F>& q_in, bool negate = false) {
 }
 
 // acc += b  (both XYZZ)
-template <class F>
+template <class F, class O = InlineOps>
 HD void ec_add(XYZZ<F>& acc, const XYZZ<F>& b) {
     if (b.is_inf()) return;
     if (acc.is_inf()) {
         acc = b;
         return;
     }
-    F u1 = fp_mul(acc.x, b.zz);
-    F u2 = fp_mul(b.x, acc.zz);
-    F s1 = fp_mul(acc.y, b.zzz);
-    F s2 = fp_mul(b.y, acc.zzz);
+    F u1 = O::mul(acc.x, b.zz);
+    F u2 = O::mul(b.x, acc.zz);
+    F s1 = O::mul(acc.y, b.zzz);
+    F s2 = O::mul(b.y, acc.zzz);
     F p = fp_sub(u2, u1);
     F r = fp_sub(s2, s1);
     if (p.is_zero()) {
@@ -153,15 +153,15 @@ HD void ec_add(XYZZ<F>& acc, const XYZZ<F>& b) {
         else acc = XYZZ<F>::inf();
         return;
     }
-    F pp = fp_sqr(p);
-    F ppp = fp_mul(p, pp);
-    F qq = fp_mul(u1, pp);
-    F x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-    F y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
+    F pp = O::sqr(p);
+    F ppp = O::mul(p, pp);
+    F qq = O::mul(u1, pp);
+    F x3 = fp_sub(fp_sub(O::sqr(r), ppp), fp_dbl(qq));
+    F y3 = fp_sub(O::mul(r, fp_sub(qq, x3)), O::mul(s1, ppp));
     acc.x = x3;
     acc.y = y3;
-    acc.zz = fp_mul(fp_mul(acc.zz, b.zz), pp);
-    acc.zzz = fp_mul(fp_mul(acc.zzz, b.zzz), ppp);
+    acc.zz = O::mul(O::mul(acc.zz, b.zz), pp);
+    acc.zzz = O::mul(O::mul(acc.zzz, b.zzz), ppp);
 }
 
 template <class F>

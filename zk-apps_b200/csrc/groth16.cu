@@ -382,8 +382,11 @@ int groth16_prove_begin(b200zk_ctx* ctx, const b200zk_pk* pk, size_t batch, cons
 }
 
 // d_z: batch * num_vars Fr (Montgomery).  groth16_prove_begin must have been called for this batch.
-int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, uint8_t* proofs_out,
-                         uint8_t* points_out) {
+// Enqueues the whole batch on the active lane's main stream and the shared MSM / assembly streams; the proof bytes
+// (and points) are copied to proofs_out / points_out by the last operations on the main stream.  Does NOT
+// synchronise the host: with pinned destinations the call returns while the GPU is still at the witness.
+int groth16_prove_enqueue(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, uint8_t* proofs_out,
+                          uint8_t* points_out) {
     const uint32_t n = 1u << pk->log_n, nv = pk->num_inputs + pk->num_aux;
     const size_t B = batch;
     void *d_abc, *d_rs, *d_msm1, *d_msm2, *d_t1, *d_t2, *d_u1, *d_proofs, *d_points = nullptr;
@@ -472,8 +475,16 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
         B200ZK_TRY(check_launch(ctx, "h_pointwise"));
     }
     B200ZK_TRY(ntt_device(ctx, abc, pk->log_n, true, &g, B));
-    B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B, 0));
+    // the h MSM has a stream of its own among the shared MSM streams (slot 5): with two batches in flight the
+    // main stream of the other lane must not queue behind it, and its scratch is then shared through the stream
     if (cc) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_h, ctx->stream));
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[4], ctx->ev_h, 0));
+    }
+    B200ZK_TRY(msm_device<Fq>(ctx, &pk->h_query, (const uint32_t*)abc, n - 1, n, B, true, m1 + 3 * B, cc ? 5 : 0));
+    if (cc) {
+        B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[4], ctx->aux[4]));  // slot 5: h
+        B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[4], 0));
         B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[2], ctx->aux[2]));  // slot 3: l
         B200ZK_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[2], 0));
         B200ZK_CUDA(ctx, cudaEventRecord(ctx->ev_join[0], fin));          // fin has waited for a
@@ -492,6 +503,12 @@ int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, si
     }
     B200ZK_CUDA(ctx, cudaMemcpyAsync(proofs_out, d_proofs, B * 192, cudaMemcpyDeviceToHost, ctx->stream));
     if (points_out) B200ZK_CUDA(ctx, cudaMemcpyAsync(points_out, d_points, B * 384, cudaMemcpyDeviceToHost, ctx->stream));
+    return B200ZK_OK;
+}
+
+int groth16_prove_device(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, size_t batch, uint8_t* proofs_out,
+                         uint8_t* points_out) {
+    B200ZK_TRY(groth16_prove_enqueue(ctx, pk, d_z, batch, proofs_out, points_out));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
 }
@@ -778,6 +795,8 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
                                uint8_t* points_out) {
     if (!ctx || !pk || !assignments || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
     if (batch == 0) return B200ZK_OK;
+    for (auto& pb : ctx->pending)
+        if (pb.active) return fail(ctx, B200ZK_ERR_BAD_ARG, "a submitted batch is still in flight: b200zk_prove_wait first");
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nv = pk->num_inputs + pk->num_aux;
     const Fr* dz = (const Fr*)assignments;
@@ -791,36 +810,113 @@ int b200zk_groth16_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const void*
     return groth16_prove_device(ctx, pk, dz, batch, proofs_out, points_out);
 }
 
-static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, int inputs_on_device,
-                                  size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
-                                  uint8_t* out_status, int relation = host::RELATION_UPDATE_NOTE) {
-    if (!ctx || !pk || !inputs || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
+static int grow_pinned(b200zk_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return B200ZK_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    B200ZK_CUDA(ctx, cudaMallocHost(p, need + need / 4));
+    *cap = need + need / 4;
+    return B200ZK_OK;
+}
+
+// Enqueue one batch (witness generation + proving) on the next free lane.  Host buffers are staged through pinned
+// memory owned by the library, so nothing here waits for the GPU and the caller's input buffers are free again on
+// return; proofs_out / out_status are filled by b200zk_prove_wait.
+static int relation_prove_submit(b200zk_ctx* ctx, const b200zk_pk* pk, int relation, const uint8_t* inputs,
+                                 int inputs_on_device, size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                 uint8_t* out_status, uint64_t* ticket) {
+    if (!ctx || !pk || !inputs || !r || !s || !proofs_out || !ticket) return B200ZK_ERR_BAD_ARG;
     if (pk->relation != relation) return fail(ctx, B200ZK_ERR_BAD_ARG, "the proving key belongs to the other relation");
-    if (batch == 0) return B200ZK_OK;
+    if (batch == 0) return fail(ctx, B200ZK_ERR_BAD_ARG, "empty batch");
+    const int lane = (int)(ctx->next_ticket & 1);
+    b200zk_ctx::PendingBatch& pb = ctx->pending[lane];
+    if (pb.active)
+        return fail(ctx, B200ZK_ERR_BAD_ARG, "two batches are already in flight: b200zk_prove_wait(ticket " +
+                                                 std::to_string(pb.ticket) + ") first");
     B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t H = pk->tree_height, nv = pk->num_inputs + pk->num_aux;
     const size_t in_bytes = batch * (size_t)pk->inputs_per_instance * 32;
+    B200ZK_TRY(grow_pinned(ctx, (void**)&pb.h_proofs, &pb.h_proofs_cap, batch * 192));
+    B200ZK_TRY(grow_pinned(ctx, (void**)&pb.h_status, &pb.h_status_cap, batch * 4));
+    B200ZK_TRY(grow_pinned(ctx, (void**)&pb.h_in, &pb.h_in_cap, (inputs_on_device ? 0 : in_bytes) + 2 * batch * 32));
+    uint8_t* h_r = pb.h_in;
+    uint8_t* h_s = h_r + batch * 32;
+    uint8_t* h_inputs = h_s + batch * 32;
+    memcpy(h_r, r, batch * 32);
+    memcpy(h_s, s, batch * 32);
+    if (!inputs_on_device) memcpy(h_inputs, inputs, in_bytes);
+    set_lane(ctx, lane);
+    struct LaneGuard {  // every other entry point works on lane 0
+        b200zk_ctx* c;
+        ~LaneGuard() { set_lane(c, 0); }
+    } guard{ctx};
     void *din = (void*)inputs, *dz, *dst;
     if (!inputs_on_device) B200ZK_TRY(scratch(ctx, "wit_in", in_bytes, &din));
     B200ZK_TRY(scratch(ctx, "g16_z", batch * (size_t)nv * sizeof(Fr), &dz));
     B200ZK_TRY(scratch(ctx, "wit_status", batch * 4, &dst));
     if (!inputs_on_device)
-        B200ZK_CUDA(ctx, cudaMemcpyAsync(din, inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    B200ZK_TRY(groth16_prove_begin(ctx, pk, batch, r, s));
+        B200ZK_CUDA(ctx, cudaMemcpyAsync(din, h_inputs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200ZK_TRY(groth16_prove_begin(ctx, pk, batch, h_r, h_s));
     B200ZK_TRY(relation_witness_device(ctx, pk->relation, pk->kind, H, nv, (const Fr*)din, batch, (Fr*)dz, (uint32_t*)dst));
-    std::vector<uint32_t> st(batch);
-    B200ZK_CUDA(ctx, cudaMemcpyAsync(st.data(), dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    B200ZK_CUDA(ctx, cudaMemcpyAsync(pb.h_status, dst, batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // An unsatisfied instance is an error, not a proof (ark: SynthesisError::Unsatisfiable) -- it is reported by
+    // b200zk_prove_wait; the batch is proven regardless so that the host never has to wait for the witness here.
+    B200ZK_TRY(groth16_prove_enqueue(ctx, pk, (const Fr*)dz, batch, pb.h_proofs, nullptr));
+    B200ZK_CUDA(ctx, cudaEventRecord(ctx->lane_done[lane], ctx->stream));
+    pb.active = true;
+    pb.ticket = ctx->next_ticket++;
+    pb.batch = batch;
+    pb.proofs_out = proofs_out;
+    pb.status_out = out_status;
+    *ticket = pb.ticket;
+    return B200ZK_OK;
+}
+
+static int prove_wait(b200zk_ctx* ctx, uint64_t ticket) {
+    if (!ctx) return B200ZK_ERR_BAD_ARG;
+    b200zk_ctx::PendingBatch& pb = ctx->pending[ticket & 1];
+    if (!pb.active || pb.ticket != ticket) return fail(ctx, B200ZK_ERR_BAD_ARG, "no batch with this ticket is in flight");
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
+    pb.active = false;
+    B200ZK_CUDA(ctx, cudaEventSynchronize(ctx->lane_done[ticket & 1]));
     bool bad = false;
-    for (size_t i = 0; i < batch; i++) {
-        if (out_status) out_status[i] = (uint8_t)st[i];
-        if (st[i] & 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "witness layout does not match the R1CS (internal error)");
-        bad = bad || (st[i] & 1);
+    for (size_t i = 0; i < pb.batch; i++) {
+        if (pb.status_out) pb.status_out[i] = (uint8_t)pb.h_status[i];
+        if (pb.h_status[i] & 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "witness layout does not match the R1CS (internal error)");
+        bad = bad || (pb.h_status[i] & 1);
     }
     // like arkworks, an unsatisfied instance is an error, not a proof (SynthesisError::Unsatisfiable in debug builds)
     if (bad) return fail(ctx, B200ZK_ERR_UNSATISFIED, "a witness does not satisfy the relation");
-    return groth16_prove_device(ctx, pk, (const Fr*)dz, batch, proofs_out, nullptr);
+    memcpy(pb.proofs_out, pb.h_proofs, pb.batch * 192);
+    return B200ZK_OK;
 }
+
+static int prove_update_note_impl(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, int inputs_on_device,
+                                  size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                  uint8_t* out_status, int relation = host::RELATION_UPDATE_NOTE) {
+    if (!ctx || !pk || !inputs || !r || !s || !proofs_out) return B200ZK_ERR_BAD_ARG;
+    if (batch == 0) return B200ZK_OK;
+    uint64_t ticket = 0;
+    B200ZK_TRY(relation_prove_submit(ctx, pk, relation, inputs, inputs_on_device, batch, r, s, proofs_out, out_status, &ticket));
+    return prove_wait(ctx, ticket);
+}
+
+int b200zk_update_note_prove_submit(b200zk_ctx* ctx, const b200zk_pk* pk, const void* inputs, int inputs_on_device,
+                                    size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                    uint8_t* out_status, uint64_t* ticket) {
+    return relation_prove_submit(ctx, pk, host::RELATION_UPDATE_NOTE, (const uint8_t*)inputs, inputs_on_device, batch, r, s,
+                                 proofs_out, out_status, ticket);
+}
+
+int b200zk_update_account_prove_submit(b200zk_ctx* ctx, const b200zk_pk* pk, const void* inputs, int inputs_on_device,
+                                       size_t batch, const uint8_t* r, const uint8_t* s, uint8_t* proofs_out,
+                                       uint8_t* out_status, uint64_t* ticket) {
+    return relation_prove_submit(ctx, pk, host::RELATION_UPDATE_ACCOUNT, (const uint8_t*)inputs, inputs_on_device, batch, r, s,
+                                 proofs_out, out_status, ticket);
+}
+
+int b200zk_prove_wait(b200zk_ctx* ctx, uint64_t ticket) { return prove_wait(ctx, ticket); }
 
 int b200zk_update_note_prove_batch(b200zk_ctx* ctx, const b200zk_pk* pk, const uint8_t* inputs, size_t batch,
                                    const uint8_t* r, const uint8_t* s, uint8_t* proofs_out, uint8_t* out_status) {

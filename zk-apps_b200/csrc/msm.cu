@@ -477,6 +477,31 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
     if (t == 0) W_out = v;
 }
 
+// The same two sums over a short segment, laid out for THROUGHPUT instead of depth: one thread per segment of
+// RED_CHUNK consecutive buckets and nothing but the two running sums -- 2 additions per bucket, the minimum, no
+// scan and no shared memory.  A batch of proofs has hundreds of bucket sets to reduce at once (128 proofs x 5 MSMs
+// x 2,048 buckets), so there is parallelism to spare, and the reduction usually runs beside the bucket accumulation
+// of another MSM: what matters there is how few SM cycles it takes away, not its own latency.  (The 256-thread
+// scan version below does 2.2x the additions and holds half an SM per CTA for milliseconds; measured
+// 8.0 ms per step serialised.)  The per-set tail (msm_seg_combine over nb / RED_CHUNK partial sums) stays log-depth.
+constexpr uint32_t RED_CHUNK = 16;
+template <class F>
+__global__ void __launch_bounds__(128) msm_chunk_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t n_chunks,
+                                                        XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ R) {
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= n_chunks) return;
+    const XYZZ<F>* B = buckets + (size_t)chunk * RED_CHUNK;
+    XYZZ<F> run = XYZZ<F>::inf(), w = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int i = (int)RED_CHUNK - 1; i >= 0; i--) {
+        const XYZZ<F> b = B[i];
+        ec_add<F, CallOps>(run, b);
+        ec_add<F, CallOps>(w, run);
+    }
+    W[chunk] = w;
+    R[chunk] = run;
+}
+
 // segment g of set s covers buckets [g*seg, (g+1)*seg): W[s*segs+g] = sum_i (i+1) B_i, R[...] = sum_i B_i
 template <class F>
 __global__ void __launch_bounds__(RED_THREADS) msm_seg_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t seg,
@@ -720,7 +745,11 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     static const int red_env = getenv("B200ZK_RED_THREADS") ? atoi(getenv("B200ZK_RED_THREADS")) : 0;
     uint32_t red_threads = RED_THREADS;
     if (red_env == 32 || red_env == 64 || red_env == 128 || red_env == 256) red_threads = (uint32_t)red_env;
-    const uint32_t seg = std::min(pl.nb, red_threads * 8), segs = pl.nb / seg;
+    // small windows (a batch of proofs: c <= 13): throughput layout, RED_CHUNK buckets per thread; large windows
+    // (one big MSM, few sets): the scan-shaped CTA per 2,048 buckets
+    static const int chunk_env = getenv("B200ZK_RED_CHUNKED") ? atoi(getenv("B200ZK_RED_CHUNKED")) : 1;
+    const bool chunked = chunk_env && pl.nb >= RED_CHUNK && pl.nb / RED_CHUNK <= RED_THREADS && red_env == 0;
+    const uint32_t seg = chunked ? RED_CHUNK : std::min(pl.nb, red_threads * 8), segs = pl.nb / seg;
     uint32_t log_seg = 0;
     while ((1u << log_seg) < seg) log_seg++;
     if (segs > RED_THREADS) return fail(ctx, B200ZK_ERR_BAD_ARG, "window too large for the bucket reduction");
@@ -738,9 +767,14 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         }
         XYZZ<F>* Wseg = (XYZZ<F>*)d_red_a;
         XYZZ<F>* Rseg = Wseg + (size_t)sets * segs;
-        msm_seg_reduce<F><<<sets * segs, red_threads, (size_t)red_threads * sizeof(XYZZ<F>), st>>>(
-            (const XYZZ<F>*)d_buckets, seg, Wseg, Rseg);
-        B200ZK_TRY(check_launch(ctx, "msm_seg_reduce"));
+        if (chunked) {
+            msm_chunk_reduce<F><<<div_up((size_t)sets * segs, 128), 128, 0, st>>>((const XYZZ<F>*)d_buckets, sets * segs, Wseg, Rseg);
+            B200ZK_TRY(check_launch(ctx, "msm_chunk_reduce"));
+        } else {
+            msm_seg_reduce<F><<<sets * segs, red_threads, (size_t)red_threads * sizeof(XYZZ<F>), st>>>(
+                (const XYZZ<F>*)d_buckets, seg, Wseg, Rseg);
+            B200ZK_TRY(check_launch(ctx, "msm_seg_reduce"));
+        }
         XYZZ<F>* src = Wseg;
         if (segs > 1) {
             msm_seg_combine<F><<<sets, comb_threads, (size_t)comb_threads * sizeof(XYZZ<F>), st>>>(

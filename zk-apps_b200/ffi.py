@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
             "b200zk_update_account_r1cs": (i32, [i32, C.POINTER(vp)]),
             "b200zk_update_account_witness_batch": (i32, [vp, vp, vp, sz, vp, vp, vp]),
             "b200zk_update_account_prove_batch": (i32, [vp, vp, vp, sz, vp, vp, vp, vp]),
+            "b200zk_update_note_prove_submit": (i32, [vp, vp, vp, i32, sz, vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
+            "b200zk_update_account_prove_submit": (i32, [vp, vp, vp, i32, sz, vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
+            "b200zk_prove_wait": (i32, [vp, C.c_uint64]),
             "b200zk_r1cs_free": (None, [vp]),
             "b200zk_r1cs_shape": (i32, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64 * 3)]),
@@ -883,6 +886,35 @@ class Groth16:
                                                               rb.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p),
                                                               proofs.ctypes.data_as(C.c_void_p), None))
         return proofs
+
+    @staticmethod
+    def prove_submit(pk: ProvingKey, inputs, rb: np.ndarray, sb: np.ndarray, batch: int, proofs: np.ndarray,
+                     status: np.ndarray | None = None, device_ptr: int | None = None) -> int:
+        """Asynchronous form (b200zk_*_prove_submit): enqueue witness generation + proving of one batch and return a
+        ticket; `proofs` (batch x 192 B uint8) and `status` are filled by prove_wait(ticket) and must stay alive until
+        then.  inputs: host rows (bytes / uint8 array) or, with device_ptr, rows already in device memory.
+        Up to two batches in flight."""
+        ctx = pk.ctx
+        if device_ptr is not None:
+            pi, on_dev = C.c_void_p(device_ptr), 1
+        else:
+            pi, ki = _buf(inputs)
+            on_dev = 0
+            if ki.nbytes != batch * pk.relation.n_inputs_per_proof * 32:
+                raise ValueError("inputs do not match the batch size")
+        if rb.nbytes != batch * 32 or sb.nbytes != batch * 32 or proofs.nbytes != batch * 192:
+            raise ValueError("r / s / proofs do not match the batch size")
+        fn = (lib().b200zk_update_account_prove_submit if isinstance(pk.relation, UpdateAccountRelation)
+              else lib().b200zk_update_note_prove_submit)
+        t = C.c_uint64()
+        ctx.check(fn(ctx.handle, pk._h, pi, on_dev, batch, rb.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p),
+                     proofs.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p) if status is not None else None,
+                     C.byref(t)))
+        return t.value
+
+    @staticmethod
+    def prove_wait(pk: ProvingKey, ticket: int):
+        pk.ctx.check(lib().b200zk_prove_wait(pk.ctx.handle, ticket))
 
     @staticmethod
     def create_random_proof(pk: ProvingKey, inputs, rng):
