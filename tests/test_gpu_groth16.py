@@ -303,3 +303,23 @@ def test_async_submit_wait_matches_the_synchronous_call(ctx, withdraw_key):
     assert e.value.code == -6 and list(st) == [1, 0, 0, 0, 0] and not out.any()
     # the ctx is usable afterwards, synchronous calls included
     assert bytes(z.Groth16.prove_update_note(pk, sets[1], rs, ss, B)[0]) == want[1]
+
+
+def test_proofs_over_full_digit_tables(ctx, withdraw_key):
+    """A key uploaded with precompute level 2 (full digit tables, here with small windows so that they are megabytes,
+    not the 135 GB of the bench configuration) gives the same proof bytes as the bucket-method key."""
+    relation, pk, M, sc = withdraw_key
+    ctx.set_option("table_c_g1", 4); ctx.set_option("table_c_g2", 3)
+    pk2 = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
+                                                         precompute=2)
+    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 11)
+    B = 6
+    ws = [rel.make_witness(300 + i, rel.WITHDRAW) for i in range(B)]
+    inputs = util.fr_mont_array([v for w in ws for v in rel.witness_to_inputs(w)])
+    rs = util.rand_fr(41, B); ss = util.rand_fr(42, B)
+    want, _ = z.Groth16.prove_update_note(pk, inputs, rs, ss, B)
+    got, status = z.Groth16.prove_update_note(pk2, inputs, rs, ss, B)
+    assert list(status) == [0] * B and bytes(got) == bytes(want)
+    zz = rel.synthesize_update_note(ws[0]).z
+    assert bytes(got[:192]) == og.proof_to_bytes(og.proof_via_scalars(M, sc, TOX, zz, rs[0], ss[0]))
+    pk2.free()

@@ -175,3 +175,32 @@ def test_glv_path_equals_full_length_path(ctx, group):
         ctx.set_option("msm_glv", 1)
         out, _ = z.VariableBaseMSM.msm_bigint(ctx, group, pts, util.scalars_array([s] * n))
         assert dec(out)[0] == cv.mul(cv.gen, sum(ks) % R * s % R)
+
+
+@pytest.mark.parametrize("group,n,c", [(1, 300, 5), (1, 77, 8), (2, 120, 4)])
+def test_full_digit_table_msm(ctx, group, n, c):
+    """precompute level 2: the full digit table (m + 1) 2^(c w) P_i resident in HBM; an MSM is then a plain sum of one
+    table entry per non-zero signed digit (no buckets).  Same bytes as the bucket method, batched, with bases at
+    infinity, zero / one / r - 1 scalars and a proof whose scalars are all zero."""
+    ks = util.rand_fr_bytes_fast(300 + n, n)
+    pts = ctx.fixed_base_mul(group, ks).copy()
+    pt = 96 if group == 1 else 192
+    pts[3 * pt:4 * pt] = 0                                           # a base at infinity
+    batch = 4
+    ss = util.rand_fr_bytes_fast(400 + n, batch * n).reshape(batch, n, 32).copy()
+    ss[0, 0] = 0; ss[0, 1] = np.frombuffer((1).to_bytes(32, "little"), dtype=np.uint8)
+    ss[0, 2] = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint8)
+    ss[2] = 0                                                        # an MSM of the batch with nothing to add
+    plain = z.VariableBaseMSM.Bases(ctx, group, pts)
+    want, want_inf = plain.msm(ss.reshape(-1), n=n, batch=batch)
+    ctx.set_option("table_c_g1" if group == 1 else "table_c_g2", c)
+    full = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=2)
+    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 11)
+    got, got_inf = full.msm(ss.reshape(-1), n=n, batch=batch)
+    assert bytes(got) == bytes(want) and list(got_inf) == list(want_inf) and got_inf[2] == 1
+    one, _ = full.msm(ss[1].reshape(-1), n=n)                        # batch of one, host scalars
+    assert bytes(one) == bytes(want[pt:2 * pt])
+    few, _ = full.msm(ss[3, :10].reshape(-1), n=10)                  # fewer scalars than bases
+    ref, _ = plain.msm(ss[3, :10].reshape(-1), n=10)
+    assert bytes(few) == bytes(ref)
+    plain.free(); full.free()

@@ -80,6 +80,11 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
         ctx->msm_glv = value != 0;
         return B200ZK_OK;
     }
+    if (strcmp(name, "table_c_g1") == 0 || strcmp(name, "table_c_g2") == 0) {  // window of full digit tables built from now on
+        if (value < 2 || value > 16) return fail(ctx, B200ZK_ERR_BAD_ARG, "table window must be 2..16");
+        (name[9] == '1' ? ctx->table_c_g1 : ctx->table_c_g2) = value;
+        return B200ZK_OK;
+    }
     return fail(ctx, B200ZK_ERR_BAD_ARG, std::string("unknown option ") + name);
 }
 

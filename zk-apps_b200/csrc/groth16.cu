@@ -308,6 +308,7 @@ void free_pk(b200zk_pk* pk) {
     {
         if (h->d_points) cudaFree(h->d_points);
         if (h->d_skip) cudaFree(h->d_skip);
+        if (h->d_table) cudaFree(h->d_table);
     }
     if (pk->d_singles) cudaFree(pk->d_singles);
     if (pk->d_delta_tab) cudaFree(pk->d_delta_tab);

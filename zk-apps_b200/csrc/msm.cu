@@ -38,6 +38,8 @@ struct Plan {
     bool precomp;
     uint32_t w0, w1;              // windows [w0, w1) this pass of the pipeline handles (all of them unless split)
     bool glv;                     // plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
+    bool table = false;           // precompute level 2: full digit table, "bucket" = the whole MSM of one proof
+    uint32_t mult = 0;            // table entries per (window, base) = 2^(c-1)
 };
 
 // Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
@@ -265,22 +267,51 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* p) {
 // (slot = seg_off[bucket] + run - first_run_of_bucket) folded by msm_fold_small / msm_fold_big.
 constexpr uint32_t FOLD_SMALL_MAX = 8;
 
+// The run length is fixed ON THE DEVICE from the real entry count (the host only knows an upper bound and never
+// waits for the count): every thread does the same number of mixed additions, so a launch is a sequence of waves of
+// equal-duration CTAs and a partially filled last wave is pure loss (15.0 M entries in 64-entry runs = 4.4 waves of
+// 444 resident CTAs: 12 % of the launch idle).  L is chosen so that the runs fill a whole number of waves: the
+// nearest whole number of waves at the host's guess L0, then L = ceil(total / (lanes per wave * waves)), kept within
+// [L0 / 2, 2 L0].
+struct RunPlan {
+    uint32_t L;       // entries per run
+    uint32_t n_runs;  // ceil(total / L)
+};
+
+__global__ void msm_plan_runs(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t L0, uint32_t lanes_per_wave,
+                              RunPlan* __restrict__ plan) {
+    const uint32_t total = offsets[n_keys];
+    uint32_t L = L0;
+    if (total && lanes_per_wave) {
+        const uint64_t per_wave = (uint64_t)lanes_per_wave * L0;
+        uint64_t waves = (total + per_wave / 2) / per_wave;
+        if (waves == 0) waves = 1;
+        const uint64_t lanes = lanes_per_wave * waves;
+        L = (uint32_t)((total + lanes - 1) / lanes);
+        const uint32_t lo = L0 > 1 ? L0 / 2 : 1, hi = 2 * L0;
+        L = L < lo ? lo : (L > hi ? hi : L);
+    }
+    plan->L = L;
+    plan->n_runs = total ? (total + L - 1) / L : 0;
+}
+
 // number of runs each bucket intersects (0 for an empty bucket)
-__global__ void msm_seg_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t log_tl,
+__global__ void msm_seg_counts(const uint32_t* __restrict__ offsets, uint32_t n_keys, const RunPlan* __restrict__ plan,
                                uint32_t* __restrict__ scount) {
     uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
+    const uint32_t L = plan->L;
     const uint32_t lo = offsets[key], hi = offsets[key + 1];
-    scount[key] = hi > lo ? ((hi - 1) >> log_tl) - (lo >> log_tl) + 1 : 0;
+    scount[key] = hi > lo ? (hi - 1) / L - lo / L + 1 : 0;
 }
 
 template <class F>
-__device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_t log_tl, const XYZZ<F>& acc,
+__device__ __forceinline__ void flush_bucket(uint32_t key, uint32_t run, uint32_t L, const XYZZ<F>& acc,
                                              const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ soff,
                                              XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ partials) {
     const uint32_t s0 = soff[key], ns = soff[key + 1] - s0;
     if (ns == 1) buckets[key] = acc;
-    else partials[s0 + (run - (offsets[key] >> log_tl))] = acc;
+    else partials[s0 + (run - offsets[key] / L)] = acc;
 }
 
 template <class F, int MIN_BLOCKS, class O>
@@ -289,15 +320,16 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
                                                       const uint32_t* __restrict__ offsets,
                                                       const uint32_t* __restrict__ sorted,
                                                       const uint32_t* __restrict__ soff, uint32_t n_keys,
-                                                      uint32_t log_tl, XYZZ<F>* __restrict__ buckets,
+                                                      const RunPlan* __restrict__ plan, XYZZ<F>* __restrict__ buckets,
                                                       XYZZ<F>* __restrict__ partials) {
-    // the grid is sized for the worst case; the real entry count lives in device memory so the
-    // host never has to wait for it
+    // the grid is sized for the worst case; the real entry count and the run length derived from it live in
+    // device memory so the host never has to wait for them
     const uint32_t run = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t L = plan->L;
+    if (run >= plan->n_runs) return;
     const uint32_t total = offsets[n_keys];
-    uint32_t k = run << log_tl;
-    if (k >= total) return;
-    const uint32_t end = min(k + (1u << log_tl), total);
+    uint32_t k = run * L;
+    const uint32_t end = min(k + L, total);
     // bucket of the first entry: the last key with offsets[key] <= k (skips empty buckets)
     uint32_t lo = 0, hi = n_keys;  // invariant: offsets[lo] <= k < offsets[hi]
     while (hi - lo > 1) {
@@ -339,7 +371,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         ec_madd<F, O>(acc, cur, neg);
         if (kn >= end) break;
         if (kn == bend) {  // next entry belongs to a later bucket
-            flush_bucket(key, run, log_tl, acc, offsets, soff, buckets, partials);
+            flush_bucket(key, run, L, acc, offsets, soff, buckets, partials);
             acc = XYZZ<F>::inf();
             do {
                 key++;
@@ -351,7 +383,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         neg = (vn >> 31) != 0;
         k = kn;
     }
-    flush_bucket(key, run, log_tl, acc, offsets, soff, buckets, partials);
+    flush_bucket(key, run, L, acc, offsets, soff, buckets, partials);
 }
 
 // thread per bucket: empty -> infinity, <= FOLD_SMALL_MAX partials -> summed here, more -> queued
@@ -375,7 +407,7 @@ __global__ void __launch_bounds__(64) msm_fold_small(const uint32_t* __restrict_
     XYZZ<F> acc = partials[lo];
     for (uint32_t t = 1; t < nt; t++) {
         XYZZ<F> b = partials[lo + t];
-        ec_add(acc, b);
+        ec_add<F, CallOps>(acc, b);
     }
     buckets[key] = acc;
 }
@@ -395,14 +427,14 @@ __global__ void __launch_bounds__(32) msm_fold_big(const uint32_t* __restrict__ 
         XYZZ<F> acc = XYZZ<F>::inf();
         for (uint32_t t = lane; t < nt; t += 32) {
             XYZZ<F> b = partials[lo + t];
-            ec_add(acc, b);
+            ec_add<F, CallOps>(acc, b);
         }
         sh[lane] = acc;
         __syncwarp();
         for (uint32_t step = 16; step >= 1; step >>= 1) {
             if (lane < step) {
                 XYZZ<F> b = sh[lane + step];
-                ec_add(acc, b);
+                ec_add<F, CallOps>(acc, b);
                 sh[lane] = acc;
             }
             __syncwarp();
@@ -436,8 +468,8 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
         const XYZZ<F>* B = items + (size_t)t * I;
         for (int i = (int)I - 1; i >= 0; i--) {
             XYZZ<F> b = B[i];
-            ec_add(run, b);
-            ec_add(w, run);
+            ec_add<F, CallOps>(run, b);
+            ec_add<F, CallOps>(w, run);
         }
     }
     // inclusive suffix scan of `run`
@@ -451,7 +483,7 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
         if (has) other = sh[t + d];
         __syncthreads();
         if (has) {
-            ec_add(x, other);
+            ec_add<F, CallOps>(x, other);
             sh[t] = x;
         }
         __syncthreads();
@@ -460,7 +492,7 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
     if (t >= 1 && t < active) {
         XYZZ<F> s = x;
         for (uint32_t d = 0; d < log_i; d++) s = ec_dbl(s);
-        ec_add(v, s);
+        ec_add<F, CallOps>(v, s);
     }
     if (t == 0) R_out = x;
     __syncthreads();
@@ -469,7 +501,7 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
     for (uint32_t step = T >> 1; step >= 1; step >>= 1) {
         if (t < step && t + step < active) {
             XYZZ<F> b = sh[t + step];
-            ec_add(v, b);
+            ec_add<F, CallOps>(v, b);
             sh[t] = v;
         }
         __syncthreads();
@@ -485,21 +517,43 @@ __device__ void block_weighted_sum(const XYZZ<F>* __restrict__ items, uint32_t m
 // scan version below does 2.2x the additions and holds half an SM per CTA for milliseconds; measured
 // 8.0 ms per step serialised.)  The per-set tail (msm_seg_combine over nb / RED_CHUNK partial sums) stays log-depth.
 constexpr uint32_t RED_CHUNK = 16;
+// The fold of the accumulation's partial sums is fused in: a bucket written whole by one run (or folded by
+// msm_fold_big because it is huge) is read from `buckets`, an empty one is the identity, and a bucket split over a
+// few runs is summed from its partials right here -- one launch and one pass over the buckets less per MSM.
 template <class F>
-__global__ void __launch_bounds__(128) msm_chunk_reduce(const XYZZ<F>* __restrict__ buckets, uint32_t n_chunks,
+__global__ void __launch_bounds__(128) msm_chunk_reduce(const XYZZ<F>* __restrict__ buckets,
+                                                        const XYZZ<F>* __restrict__ partials,
+                                                        const uint32_t* __restrict__ toff, uint32_t n_chunks,
                                                         XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ R) {
     const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
     if (chunk >= n_chunks) return;
-    const XYZZ<F>* B = buckets + (size_t)chunk * RED_CHUNK;
+    const uint32_t key0 = chunk * RED_CHUNK;
     XYZZ<F> run = XYZZ<F>::inf(), w = XYZZ<F>::inf();
 #pragma unroll 1
     for (int i = (int)RED_CHUNK - 1; i >= 0; i--) {
-        const XYZZ<F> b = B[i];
-        ec_add<F, CallOps>(run, b);
+        const uint32_t key = key0 + (uint32_t)i;
+        const uint32_t lo = toff[key], nt = toff[key + 1] - lo;
+        if (nt == 1 || nt > FOLD_SMALL_MAX) {
+            const XYZZ<F> b = buckets[key];
+            ec_add<F, CallOps>(run, b);
+        } else {
+            for (uint32_t t = 0; t < nt; t++) {
+                const XYZZ<F> b = partials[lo + t];
+                ec_add<F, CallOps>(run, b);
+            }
+        }
         ec_add<F, CallOps>(w, run);
     }
     W[chunk] = w;
     R[chunk] = run;
+}
+
+// thread per bucket: queue the buckets with more than FOLD_SMALL_MAX partials for msm_fold_big (no arithmetic here)
+__global__ void msm_fold_classify(const uint32_t* __restrict__ toff, uint32_t n_keys, uint32_t* __restrict__ big_list,
+                                  uint32_t* __restrict__ big_count) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    if (toff[key + 1] - toff[key] > FOLD_SMALL_MAX) big_list[atomicAdd(big_count, 1u)] = key;
 }
 
 // segment g of set s covers buckets [g*seg, (g+1)*seg): W[s*segs+g] = sum_i (i+1) B_i, R[...] = sum_i B_i
@@ -534,14 +588,14 @@ __global__ void __launch_bounds__(RED_THREADS) msm_seg_combine(const XYZZ<F>* __
     for (uint32_t step = blockDim.x >> 1; step >= 1; step >>= 1) {
         if (t < step) {
             XYZZ<F> b = sh[t + step];
-            ec_add(v, b);
+            ec_add<F, CallOps>(v, b);
             sh[t] = v;
         }
         __syncthreads();
     }
     if (t == 0) {
         for (uint32_t d = 0; d < log_seg; d++) hi = ec_dbl(hi);
-        ec_add(v, hi);
+        ec_add<F, CallOps>(v, hi);
         out[blockIdx.x] = v;
     }
 }
@@ -556,7 +610,7 @@ __global__ void __launch_bounds__(32) msm_finish(const XYZZ<F>* __restrict__ wsu
     for (int w = (int)weff - 2; w >= 0; w--) {
         for (uint32_t d = 0; d < c; d++) acc = ec_dbl(acc);
         XYZZ<F> s = wsums[(size_t)b * weff + w];
-        ec_add(acc, s);
+        ec_add<F, CallOps>(acc, s);
     }
     out[b] = ec_to_affine(acc);
 }
@@ -596,18 +650,140 @@ __global__ void __launch_bounds__(32) points_sum_kernel(const Affine<F>* __restr
     __shared__ XYZZ<F> sh[32];
     const uint32_t lane = threadIdx.x;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = lane; i < n; i += 32) ec_madd(acc, load_affine(pts + i));
+    for (uint32_t i = lane; i < n; i += 32) ec_madd<F, CallOps>(acc, load_affine(pts + i));
     sh[lane] = acc;
     __syncwarp();
     for (uint32_t step = 16; step >= 1; step >>= 1) {
         if (lane < step) {
             XYZZ<F> b = sh[lane + step];
-            ec_add(acc, b);
+            ec_add<F, CallOps>(acc, b);
             sh[lane] = acc;
         }
         __syncwarp();
     }
     if (lane == 0) *out = ec_to_affine(acc);
+}
+
+// ---------------------------------------------------------------- full digit tables (precompute level 2)
+// With T[(w n + i) mult + m] = (m + 1) 2^(c w) P_i resident, sum_i k_i P_i = sum over the non-zero signed digits
+// d of every scalar of  sign(d) * T[w, i, |d| - 1]: one mixed addition per digit, the same count as the bucket
+// method's accumulation, and NOTHING else -- no sort (the entries are taken in scalar order), no fold of split
+// buckets, no bucket reduction, no window combine.  The entry list of a batch is laid out proof after proof and cut
+// into equal runs exactly like the bucket-sorted list (msm_accumulate is reused unchanged, with "bucket" = proof);
+// the runs of a proof are then added by one CTA (msm_sum_partials).
+
+// number of non-zero digits of scalar (b, i)
+__global__ void table_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, uint32_t c,
+                            uint32_t windows, const uint8_t* __restrict__ skip, uint32_t* __restrict__ counts) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    const size_t b = t / n, i = t % n;
+    uint32_t cnt = 0;
+    if (!(skip && skip[i])) {
+        uint32_t k[8];
+        load_scalar(scalars, b * stride + i, mont != 0, k);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < windows; w++) cnt += next_digit(k, w, c, carry) != 0 ? 1u : 0u;
+    }
+    counts[t] = cnt;
+}
+
+// entries of scalar (b, i) at off[b n + i]...: table index | sign
+__global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, uint32_t c,
+                              uint32_t windows, uint32_t mult, const uint8_t* __restrict__ skip,
+                              const uint32_t* __restrict__ off, uint32_t* __restrict__ entries) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n * batch) return;
+    const size_t b = t / n, i = t % n;
+    if (skip && skip[i]) return;
+    uint32_t k[8];
+    load_scalar(scalars, b * stride + i, mont != 0, k);
+    uint32_t carry = 0, pos = off[t];
+    for (uint32_t w = 0; w < windows; w++) {
+        const int32_t d = next_digit(k, w, c, carry);
+        if (d == 0) continue;
+        const uint32_t m = (uint32_t)(d < 0 ? -d : d) - 1;
+        entries[pos++] = (uint32_t)(((size_t)w * n + i) * mult + m) | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+
+// poff[b] = first entry of proof b, poff[batch] = total
+__global__ void table_proof_offsets(const uint32_t* __restrict__ off, size_t n, size_t batch, uint32_t* __restrict__ poff) {
+    size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (b <= batch) poff[b] = off[b * n];
+}
+
+// one CTA per proof: sum of the partial sums its runs left (or the single whole sum), log-depth
+template <class F>
+__global__ void __launch_bounds__(128) msm_sum_partials(const uint32_t* __restrict__ toff, const XYZZ<F>* __restrict__ partials,
+                                                        const XYZZ<F>* __restrict__ whole, XYZZ<F>* __restrict__ out) {
+    extern __shared__ uint4 red_smem[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(red_smem);
+    const uint32_t key = blockIdx.x, t = threadIdx.x;
+    const uint32_t lo = toff[key], nt = toff[key + 1] - lo;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (nt == 1) {
+        if (t == 0) acc = whole[key];
+    } else {
+        for (uint32_t j = t; j < nt; j += blockDim.x) {
+            const XYZZ<F> b = partials[lo + j];
+            ec_add<F, CallOps>(acc, b);
+        }
+    }
+    sh[t] = acc;
+    __syncthreads();
+    for (uint32_t step = blockDim.x >> 1; step >= 1; step >>= 1) {
+        if (t < step) {
+            const XYZZ<F> b = sh[t + step];
+            ec_add<F, CallOps>(acc, b);
+            sh[t] = acc;
+        }
+        __syncthreads();
+    }
+    if (t == 0) out[key] = acc;
+}
+
+// table build, step 1: row r = (w, i) of the window-multiple table Q -> its first `mult` multiples as XYZZ
+template <class F>
+__global__ void __launch_bounds__(64) table_multiples(const Affine<F>* __restrict__ Q, size_t rows, uint32_t mult,
+                                                      XYZZ<F>* __restrict__ out) {
+    size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const Affine<F> q = load_affine(Q + r);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    XYZZ<F>* dst = out + r * mult;
+    for (uint32_t m = 0; m < mult; m++) {
+        ec_madd<F, CallOps>(acc, q);
+        dst[m] = acc;
+    }
+}
+
+// table build, step 2: XYZZ -> affine, TA_CHUNK points per thread sharing one inversion (Montgomery's trick)
+constexpr int TA_CHUNK = 16;
+template <class F>
+__global__ void __launch_bounds__(64) table_to_affine(const XYZZ<F>* __restrict__ in, size_t count, Affine<F>* __restrict__ out) {
+    size_t chunk = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t base = chunk * TA_CHUNK;
+    if (base >= count) return;
+    const int m = (int)(count - base < (size_t)TA_CHUNK ? count - base : (size_t)TA_CHUNK);
+    F pref[TA_CHUNK];
+    F run = F::one();
+    for (int k = 0; k < m; k++) {      // running product of the denominators zz * zzz (1 for a point at infinity)
+        const XYZZ<F> p = in[base + k];
+        pref[k] = run;
+        if (!p.is_inf()) run = fp_mul(run, fp_mul(p.zz, p.zzz));
+    }
+    F inv = fp_inv(run);
+    for (int k = m - 1; k >= 0; k--) {
+        const XYZZ<F> p = in[base + k];
+        if (p.is_inf()) {
+            out[base + k] = Affine<F>::inf();
+            continue;
+        }
+        const F zi = fp_mul(inv, pref[k]);                 // 1 / (zz zzz) of point k
+        inv = fp_mul(inv, fp_mul(p.zz, p.zzz));
+        out[base + k] = Affine<F>{fp_mul(p.x, fp_mul(zi, p.zzz)), fp_mul(p.y, fp_mul(zi, p.zz))};
+    }
 }
 
 int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, int slot, const uint32_t* d_in, size_t n,
@@ -640,6 +816,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     if (n_keys64 >= (1ull << 31) || max_entries >= (1ull << 32) || (uint64_t)h->n * pl.windows >= (1ull << 31) ||
         (pl.glv && 2 * (uint64_t)n >= (1ull << 31)))
         return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit bucket keys; split the batch");
+    if (pl.table && ((uint64_t)h->n * pl.windows * pl.mult >= (1ull << 31) || (uint64_t)batch * h->n + 1 >= (1ull << 32)))
+        return fail(ctx, B200ZK_ERR_BAD_LEN, "digit table too large for 31-bit entry indices");
     const uint32_t n_keys = (uint32_t)n_keys64;
 
     void *d_counts, *d_offsets, *d_cursor, *d_sorted, *d_buckets, *d_red_a, *d_red_b;
@@ -651,8 +829,23 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
                        (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets, slot));
 
     const size_t total = n * batch;
-    B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
-    {
+    if (pl.table) {
+        // entries in scalar order, proof after proof: per-scalar digit counts -> scan -> entries; no sort, no atomics
+        ProfScope ps(ctx, "msm_sort", st);
+        void *d_cnt, *d_off;
+        B200ZK_TRY(scratch(ctx, "msm_tab_cnt", (total + 1) * 4, &d_cnt, slot));
+        B200ZK_TRY(scratch(ctx, "msm_tab_off", (total + 1) * 4, &d_off, slot));
+        table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, h->d_skip,
+                                                        (uint32_t*)d_cnt);
+        B200ZK_TRY(check_launch(ctx, "table_count"));
+        B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
+        table_entries<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, pl.mult,
+                                                          h->d_skip, (const uint32_t*)d_off, (uint32_t*)d_sorted);
+        B200ZK_TRY(check_launch(ctx, "table_entries"));
+        table_proof_offsets<<<div_up(batch + 1, 128), 128, 0, st>>>((const uint32_t*)d_off, n, batch, (uint32_t*)d_offsets);
+        B200ZK_TRY(check_launch(ctx, "table_proof_offsets"));
+    } else {
+        B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
         ProfScope ps(ctx, "msm_sort", st);
         msm_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl, h->d_skip,
                                                                (uint32_t*)d_counts);
@@ -671,14 +864,33 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     uint32_t log_tl = 6;
     while (log_tl < 10 && (max_entries / n_keys) >= (4ull << log_tl)) log_tl++;
     while (log_tl > 3 && (max_entries >> log_tl) < 65536) log_tl--;
-    const uint64_t max_runs = (max_entries >> log_tl) + 1;
+    const uint32_t L0 = 1u << log_tl, L_min = L0 > 1 ? L0 / 2 : 1;   // msm_plan_runs picks L in [L0 / 2, 2 L0]
+    const uint64_t max_runs = max_entries / L_min + 1;
     const uint64_t max_segs = (uint64_t)n_keys + max_runs + 1;
+    // ---- which build of the accumulation kernel runs, and how many of its threads one wave holds
+    // resident CTAs per SM (register cap 65536 / (128 * blocks)); tunable for experiments
+    static const int occ_env = getenv("B200ZK_ACC_BLOCKS") ? atoi(getenv("B200ZK_ACC_BLOCKS")) : 0;
+    static const int occ2_env = getenv("B200ZK_ACC_BLOCKS_G2") ? atoi(getenv("B200ZK_ACC_BLOCKS_G2")) : occ_env;
+    const int occ_sel = sizeof(F) == sizeof(Fq) ? occ_env : occ2_env;
+    // measured (profiles/r02_acc_sweep.log, 128-proof step): with the call-based products G1 gains 8 % from a
+    // third resident CTA (24.1 -> 22.35 ms, 0.82 -> 0.885 of the Fq-mul peak; a fourth adds 0.5 % and costs the
+    // concurrent tails), G2 is best at 2 CTAs (255 registers, 12.9 ms; 168 registers spill: 13.2 ms)
+    const int occ = occ_sel ? occ_sel : (sizeof(F) == sizeof(Fq) ? 3 : 2);
+    // CTA width (<= 128): narrower CTAs leave registers for latency-bound CTAs of other MSMs (experiments)
+    static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
+    const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;
+    static const int balance_env = getenv("B200ZK_ACC_BALANCE") ? atoi(getenv("B200ZK_ACC_BALANCE")) : 1;
+    const uint32_t lanes_per_wave = (uint32_t)ctx->sm_count * (uint32_t)std::min(occ, 4) * acc_threads;
+    void* d_plan;
+    B200ZK_TRY(scratch(ctx, "msm_plan", sizeof(RunPlan), &d_plan, slot));
     B200ZK_TRY(scratch(ctx, "msm_tcount", ((size_t)n_keys + 1) * 4, &d_tcount, slot));
     B200ZK_TRY(scratch(ctx, "msm_toff", ((size_t)n_keys + 1) * 4, &d_toff, slot));
     B200ZK_TRY(scratch(ctx, "msm_big", ((size_t)max_runs / FOLD_SMALL_MAX + 8) * 4, &d_big, slot));
     {
         ProfScope ps(ctx, "msm_tasks", st);
-        msm_seg_counts<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_offsets, n_keys, log_tl,
+        msm_plan_runs<<<1, 1, 0, st>>>((const uint32_t*)d_offsets, n_keys, L0, balance_env ? lanes_per_wave : 0u, (RunPlan*)d_plan);
+        B200ZK_TRY(check_launch(ctx, "msm_plan_runs"));
+        msm_seg_counts<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_offsets, n_keys, (const RunPlan*)d_plan,
                                                             (uint32_t*)d_tcount);
         B200ZK_TRY(check_launch(ctx, "msm_seg_counts"));
         B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_tcount, n_keys, (uint32_t*)d_toff));
@@ -697,14 +909,6 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     uint32_t* big_list = (uint32_t*)d_big + 1;
     {
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_accumulate_g1" : "msm_accumulate_g2", st);
-        // resident CTAs per SM (register cap 65536 / (128 * blocks)); tunable for experiments
-        static const int occ_env = getenv("B200ZK_ACC_BLOCKS") ? atoi(getenv("B200ZK_ACC_BLOCKS")) : 0;
-        static const int occ2_env = getenv("B200ZK_ACC_BLOCKS_G2") ? atoi(getenv("B200ZK_ACC_BLOCKS_G2")) : occ_env;
-        const int occ_sel = sizeof(F) == sizeof(Fq) ? occ_env : occ2_env;
-        // measured (profiles/r02_acc_sweep.log, 128-proof step): with the call-based products G1 gains 8 % from a
-        // third resident CTA (24.1 -> 22.35 ms, 0.82 -> 0.885 of the Fq-mul peak; a fourth adds 0.5 % and costs the
-        // concurrent tails), G2 is best at 2 CTAs (255 registers, 12.9 ms; 168 registers spill: 13.2 ms)
-        const int occ = occ_sel ? occ_sel : (sizeof(F) == sizeof(Fq) ? 3 : 2);
         // how the field products are issued (ec.cuh): 0 = expanded in place, 1 = calls to one Fq product / square
         // (operands by value, in registers), 2 = G2 only: Fq2 products as calls around the Fq calls
         static const int var_env = getenv("B200ZK_ACC_VARIANT") ? atoi(getenv("B200ZK_ACC_VARIANT")) : 1;
@@ -714,41 +918,54 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         if (variant == 0) kern = occ >= 3 ? msm_accumulate<F, 3, InlineOps> : msm_accumulate<F, 2, InlineOps>;
         else if (variant == 2) kern = occ >= 3 ? msm_accumulate<F, 3, NestedCallOps> : msm_accumulate<F, 2, NestedCallOps>;
         else kern = occ >= 4 ? msm_accumulate<F, 4, CallOps> : occ == 3 ? msm_accumulate<F, 3, CallOps> : msm_accumulate<F, 2, CallOps>;
-        // CTA width (<= 128): narrower CTAs leave registers for latency-bound CTAs of other MSMs (experiments)
-        static const int thr_env = getenv("B200ZK_ACC_THREADS_G2") ? atoi(getenv("B200ZK_ACC_THREADS_G2")) : 0;
-        const unsigned acc_threads = (sizeof(F) != sizeof(Fq) && (thr_env == 64 || thr_env == 96)) ? (unsigned)thr_env : 128u;
         // experiments: a dynamic shared-memory request caps the resident CTAs per SM independently of the register
         // budget the kernel was compiled for (B200ZK_ACC_BLOCKS=3 -> 168 registers, B200ZK_ACC_SMEM_KB=100 -> 2 CTAs)
         static const int smem_kb = getenv("B200ZK_ACC_SMEM_KB") ? atoi(getenv("B200ZK_ACC_SMEM_KB")) : 0;
         if (smem_kb > 0) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
         kern<<<div_up(max_runs, acc_threads), acc_threads, (size_t)smem_kb * 1024, st>>>(
-            (const Affine<F>*)h->d_points, d_phi, pl.glv ? (uint32_t)n : 0x80000000u, (const uint32_t*)d_offsets,
-            (const uint32_t*)d_sorted,
-            (const uint32_t*)d_toff, n_keys, log_tl, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
+            (const Affine<F>*)(pl.table ? h->d_table : h->d_points), d_phi, pl.glv ? (uint32_t)n : 0x80000000u,
+            (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
+            (const uint32_t*)d_toff, n_keys, (const RunPlan*)d_plan, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
     }
+    if (pl.table) {  // the runs of a proof are all that is left to add: one CTA per proof
+        ProfScope ps(ctx, "msm_reduce", st);
+        B200ZK_TRY(scratch(ctx, "msm_red_b", ((size_t)n_keys + 8) * sizeof(XYZZ<F>), &d_red_b, slot));
+        const size_t smem = 128 * sizeof(XYZZ<F>);
+        if (smem > 48 * 1024) B200ZK_CUDA(ctx, cudaFuncSetAttribute(msm_sum_partials<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        msm_sum_partials<F><<<n_keys, 128, smem, st>>>((const uint32_t*)d_toff, (const XYZZ<F>*)d_partials,
+                                                       (const XYZZ<F>*)d_buckets, (XYZZ<F>*)d_red_b);
+        B200ZK_TRY(check_launch(ctx, "msm_sum_partials"));
+        *sums_out = (const XYZZ<F>*)d_red_b;
+        return B200ZK_OK;
+    }
+    // CTA shape of the scan-shaped reduction: 256 threads x 8 buckets.  Narrower CTAs (64 or 32 threads over 512/256-bucket
+    // segments) fit in the registers two resident msm_accumulate CTAs leave free, but measured slower for the proof batch
+    // (51.2 vs 50.3 ms per step, profiles/r01_red_sweep.log): B200ZK_RED_THREADS keeps the experiment reproducible.
+    static const int red_env = getenv("B200ZK_RED_THREADS") ? atoi(getenv("B200ZK_RED_THREADS")) : 0;
+    // small windows (a batch of proofs: c <= 13): throughput layout, RED_CHUNK buckets per thread, fold fused in; large
+    // windows (one big MSM, few sets): fold kernel + the scan-shaped CTA per 2,048 buckets
+    static const int chunk_env = getenv("B200ZK_RED_CHUNKED") ? atoi(getenv("B200ZK_RED_CHUNKED")) : 1;
+    const bool chunked = chunk_env && pl.nb >= RED_CHUNK && pl.nb / RED_CHUNK <= RED_THREADS && red_env == 0;
     {
         ProfScope ps(ctx, "msm_fold", st);
-        msm_fold_small<F><<<div_up(n_keys, 64), 64, 0, st>>>((const uint32_t*)d_toff, n_keys,
-                                                                       (const XYZZ<F>*)d_partials, (XYZZ<F>*)d_buckets,
-                                                                       big_list, big_count);
-        B200ZK_TRY(check_launch(ctx, "msm_fold_small"));
+        if (chunked) {
+            msm_fold_classify<<<div_up(n_keys, 256), 256, 0, st>>>((const uint32_t*)d_toff, n_keys, big_list, big_count);
+            B200ZK_TRY(check_launch(ctx, "msm_fold_classify"));
+        } else {
+            msm_fold_small<F><<<div_up(n_keys, 64), 64, 0, st>>>((const uint32_t*)d_toff, n_keys,
+                                                                           (const XYZZ<F>*)d_partials, (XYZZ<F>*)d_buckets,
+                                                                           big_list, big_count);
+            B200ZK_TRY(check_launch(ctx, "msm_fold_small"));
+        }
         msm_fold_big<F><<<ctx->sm_count * 4, 32, 0, st>>>((const uint32_t*)d_toff, (const XYZZ<F>*)d_partials,
                                                                    (XYZZ<F>*)d_buckets, big_list, big_count);
         B200ZK_TRY(check_launch(ctx, "msm_fold_big"));
     }
     // bucket reduction
     const uint32_t sets = (uint32_t)batch * pl.weff;
-    // CTA shape: 256 threads x 8 buckets.  Narrower CTAs (64 or 32 threads over 512/256-bucket segments) fit in the
-    // registers two resident msm_accumulate CTAs leave free, but measured slower for the proof batch (51.2 vs
-    // 50.3 ms per step, profiles/r01_red_sweep.log): B200ZK_RED_THREADS keeps the experiment reproducible.
-    static const int red_env = getenv("B200ZK_RED_THREADS") ? atoi(getenv("B200ZK_RED_THREADS")) : 0;
     uint32_t red_threads = RED_THREADS;
     if (red_env == 32 || red_env == 64 || red_env == 128 || red_env == 256) red_threads = (uint32_t)red_env;
-    // small windows (a batch of proofs: c <= 13): throughput layout, RED_CHUNK buckets per thread; large windows
-    // (one big MSM, few sets): the scan-shaped CTA per 2,048 buckets
-    static const int chunk_env = getenv("B200ZK_RED_CHUNKED") ? atoi(getenv("B200ZK_RED_CHUNKED")) : 1;
-    const bool chunked = chunk_env && pl.nb >= RED_CHUNK && pl.nb / RED_CHUNK <= RED_THREADS && red_env == 0;
     const uint32_t seg = chunked ? RED_CHUNK : std::min(pl.nb, red_threads * 8), segs = pl.nb / seg;
     uint32_t log_seg = 0;
     while ((1u << log_seg) < seg) log_seg++;
@@ -768,7 +985,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         XYZZ<F>* Wseg = (XYZZ<F>*)d_red_a;
         XYZZ<F>* Rseg = Wseg + (size_t)sets * segs;
         if (chunked) {
-            msm_chunk_reduce<F><<<div_up((size_t)sets * segs, 128), 128, 0, st>>>((const XYZZ<F>*)d_buckets, sets * segs, Wseg, Rseg);
+            msm_chunk_reduce<F><<<div_up((size_t)sets * segs, 128), 128, 0, st>>>(
+                (const XYZZ<F>*)d_buckets, (const XYZZ<F>*)d_partials, (const uint32_t*)d_toff, sets * segs, Wseg, Rseg);
             B200ZK_TRY(check_launch(ctx, "msm_chunk_reduce"));
         } else {
             msm_seg_reduce<F><<<sets * segs, red_threads, (size_t)red_threads * sizeof(XYZZ<F>), st>>>(
@@ -810,6 +1028,12 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     // (n products, one pass over the points) so the handle stays a plain array of the caller's bases
     const bool glv = !h->precomputed && ctx->msm_glv && n >= 2;
     Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0, glv);
+    if (h->d_table) {  // full digit table: one "bucket" per MSM of the batch
+        pl.table = true;
+        pl.mult = h->mult;
+        pl.weff = 1;
+        pl.nb = 1;
+    }
     const Affine<F>* d_phi = nullptr;
     if (pl.glv) {
         void* ph;
@@ -869,7 +1093,13 @@ template int msm_device<Fq2>(b200zk_ctx*, const b200zk_bases*, const uint32_t*, 
 template <class F>
 int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool src_is_device, const uint8_t* inf_flags,
                 size_t n, int precompute) {
-    Plan pl = make_plan(n, precompute != 0, 0);
+    // precompute: 0 = plain bases, 1 = window multiples 2^(c w) P_i, 2 = full digit table (m + 1) 2^(c w) P_i, m < 2^(c-1)
+    uint32_t c_table = 0;
+    if (precompute >= 2) {  // the window of a full table is set by the memory it may take, not by the operation count
+        c_table = sizeof(F) == sizeof(Fq) ? (uint32_t)ctx->table_c_g1 : (uint32_t)ctx->table_c_g2;
+        if (c_table < 2 || c_table > 16) return fail(ctx, B200ZK_ERR_BAD_ARG, "table_c_g1 / table_c_g2 must be 2..16");
+    }
+    Plan pl = make_plan(n, precompute != 0, c_table);
     h->n = n;
     h->precomputed = precompute ? 1 : 0;
     h->c = pl.c;
@@ -910,6 +1140,38 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
                                                                           t + (size_t)w * n);
             B200ZK_TRY(check_launch(ctx, "msm_precompute_step"));
         }
+    }
+    if (precompute >= 2 && n) {
+        // ---- full digit table from the window multiples Q[w][i] just built: row r = (w, i) -> (m + 1) Q[r], m < mult.
+        // Built slab by slab through an XYZZ scratch (one inversion per TA_CHUNK points); a one-off cost per key.
+        const uint32_t mult = pl.nb;
+        const size_t rows = n * (size_t)pl.windows;
+        if ((uint64_t)rows * mult >= (1ull << 31)) return fail(ctx, B200ZK_ERR_BAD_LEN, "digit table too large for 31-bit entry indices");
+        const size_t table_bytes = rows * mult * sizeof(Affine<F>);
+        cudaError_t e = cudaMalloc(&h->d_table, table_bytes);
+        if (e != cudaSuccess)
+            return fail(ctx, B200ZK_ERR_CUDA, "digit table of " + std::to_string(table_bytes >> 20) + " MiB does not fit: " +
+                                                  cudaGetErrorString(e) + " (lower table_c_g1 / table_c_g2)");
+        h->mult = mult;
+        size_t slab_rows = std::max<size_t>(1, ((size_t)2 << 30) / ((size_t)mult * sizeof(XYZZ<F>)));
+        slab_rows = std::min(slab_rows, rows);
+        void* d_x;
+        B200ZK_CUDA(ctx, cudaMalloc(&d_x, slab_rows * mult * sizeof(XYZZ<F>)));
+        const Affine<F>* Q = (const Affine<F>*)h->d_points;
+        int rc = B200ZK_OK;
+        for (size_t r0 = 0; r0 < rows && rc == B200ZK_OK; r0 += slab_rows) {
+            const size_t nr = std::min(slab_rows, rows - r0), cnt = nr * mult;
+            table_multiples<F><<<div_up(nr, 64), 64, 0, ctx->stream>>>(Q + r0, nr, mult, (XYZZ<F>*)d_x);
+            rc = check_launch(ctx, "table_multiples");
+            if (rc != B200ZK_OK) break;
+            table_to_affine<F><<<div_up(div_up(cnt, TA_CHUNK), 64), 64, 0, ctx->stream>>>((const XYZZ<F>*)d_x, cnt,
+                                                                                         (Affine<F>*)h->d_table + r0 * mult);
+            rc = check_launch(ctx, "table_to_affine");
+        }
+        cudaError_t se = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_x);
+        if (rc != B200ZK_OK) return rc;
+        if (se != cudaSuccess) return fail(ctx, B200ZK_ERR_CUDA, std::string("digit table build: ") + cudaGetErrorString(se));
     }
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host source buffers may go away
     return B200ZK_OK;
@@ -952,6 +1214,7 @@ int msm_host_entry(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8
     cudaStreamSynchronize(ctx->stream);
     if (h.d_points) cudaFree(h.d_points);
     if (h.d_skip) cudaFree(h.d_skip);
+    if (h.d_table) cudaFree(h.d_table);
     return rc;
 }
 
@@ -981,6 +1244,7 @@ int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const 
     if (rc != B200ZK_OK) {
         if (h->d_points) cudaFree(h->d_points);
         if (h->d_skip) cudaFree(h->d_skip);
+        if (h->d_table) cudaFree(h->d_table);
         delete h;
         return rc;
     }
@@ -1000,6 +1264,7 @@ int b200zk_bases_from_device(b200zk_ctx* ctx, int group, const void* d_points, s
     if (rc != B200ZK_OK) {
         if (h->d_points) cudaFree(h->d_points);
         if (h->d_skip) cudaFree(h->d_skip);
+        if (h->d_table) cudaFree(h->d_table);
         delete h;
         return rc;
     }
@@ -1015,6 +1280,7 @@ void b200zk_bases_free(b200zk_ctx* ctx, b200zk_bases* h) {
     }
     if (h->d_points) cudaFree(h->d_points);
     if (h->d_skip) cudaFree(h->d_skip);
+    if (h->d_table) cudaFree(h->d_table);
     delete h;
 }
 

@@ -386,12 +386,12 @@ class VariableBaseMSM:
             if device_ptr is not None:
                 self.n = n
                 ctx.check(lib().b200zk_bases_from_device(ctx.handle, group, C.c_void_p(device_ptr), n,
-                                                         1 if precompute else 0, C.byref(self._h)))
+                                                         int(precompute), C.byref(self._h)))
             else:
                 pb, kb = _buf(bases)
                 pf, kf = _buf(inf_flags)
                 self.n = kb.nbytes // pt
-                ctx.check(lib().b200zk_bases_upload(ctx.handle, group, pb, pf, self.n, 1 if precompute else 0,
+                ctx.check(lib().b200zk_bases_upload(ctx.handle, group, pb, pf, self.n, int(precompute),
                                                     C.byref(self._h)))
 
         def msm(self, scalars=None, n: int | None = None, batch: int = 1, device_ptr: int | None = None):
@@ -697,7 +697,7 @@ class ProvingKey:
         pd, kd = _buf(data)
         h, hv = C.c_void_p(), C.c_void_p()
         ctx.check(lib().b200zk_pk_deserialize(ctx.handle, relation.handle, pd, len(data), 1 if check_subgroup else 0,
-                                              1 if precompute else 0, C.byref(h), C.byref(hv)))
+                                              int(precompute), C.byref(h), C.byref(hv)))
         vk = VerifyingKey(ctx, handle=hv)
         raw = vk.export()
         vk.free()
@@ -841,7 +841,7 @@ class Groth16:
         h = C.c_void_p()
         vk = np.zeros(672 + relation.num_inputs * 96, dtype=np.uint8)
         pt, kt = _buf(tb)
-        ctx.check(lib().b200zk_groth16_setup(ctx.handle, relation.handle, pt, 1 if precompute else 0, C.byref(h),
+        ctx.check(lib().b200zk_groth16_setup(ctx.handle, relation.handle, pt, int(precompute), C.byref(h),
                                              vk.ctypes.data_as(C.c_void_p)))
         return ProvingKey(ctx, relation, h, vk)
 
@@ -851,7 +851,7 @@ class Groth16:
         bufs = [_buf(x) for x in (alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query, b_g2_query,
                                   l_query, h_query)]
         h = C.c_void_p()
-        ctx.check(lib().b200zk_pk_upload(ctx.handle, relation.handle, *[b[0] for b in bufs], 1 if precompute else 0,
+        ctx.check(lib().b200zk_pk_upload(ctx.handle, relation.handle, *[b[0] for b in bufs], int(precompute),
                                          C.byref(h)))
         return ProvingKey(ctx, relation, h, None)
 
