@@ -203,4 +203,7 @@ def test_full_digit_table_msm(ctx, group, n, c):
     few, _ = full.msm(ss[3, :10].reshape(-1), n=10)                  # fewer scalars than bases
     ref, _ = plain.msm(ss[3, :10].reshape(-1), n=10)
     assert bytes(few) == bytes(ref)
-    plain.free(); full.free()
+    win = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=1)      # window multiples: the same with the bucket method
+    few1, _ = win.msm(ss[3, :10].reshape(-1), n=10)
+    assert bytes(few1) == bytes(ref)
+    plain.free(); full.free(); win.free()

@@ -24,6 +24,7 @@
 // msm index is just the high part of the bucket key.
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 
 #include "glv.cuh"
 #include "types.cuh"
@@ -40,6 +41,7 @@ struct Plan {
     bool glv;                     // plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
     bool table = false;           // precompute level 2: full digit table, "bucket" = the whole MSM of one proof
     uint32_t mult = 0;            // table entries per (window, base) = 2^(c-1)
+    size_t n_table = 0;           // bases per window in a precomputed table (= bases of the handle, >= scalars of a call)
 };
 
 // Window size from an operation-count model (Fq multiplications): n*W mixed additions (10 each)
@@ -75,6 +77,7 @@ Plan make_plan(size_t n, bool precomp, uint32_t c_fixed, bool glv = false) {
     p.weff = precomp ? 1 : p.windows;
     p.w0 = 0;
     p.w1 = p.windows;
+    p.n_table = n;
     return p;
 }
 
@@ -118,7 +121,7 @@ __device__ __forceinline__ void for_each_digit(const uint32_t* k, const Plan& pl
         if (d == 0 || w < pl.w0 || w >= pl.w1) continue;
         uint32_t bucket = (uint32_t)(d < 0 ? -d : d) - 1;
         uint32_t key = (b * pl.weff + (pl.precomp ? 0 : w - pl.w0)) * pl.nb + bucket;
-        uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * n + pidx0 : pidx0);
+        uint32_t pidx = (uint32_t)(pl.precomp ? (size_t)w * pl.n_table + pidx0 : pidx0);
         f(key, pidx | (d < 0 ? 0x80000000u : 0u));
     }
 }
@@ -345,28 +348,53 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         const uint32_t idx = e & 0x7fffffffu;
         return idx < n_split ? bases + idx : bases2 + (idx - n_split);
     };
+    // How the NEXT point is fetched while the current addition runs.
+    //  * fully inlined G1 build: into registers (the load stays in flight across the straight-line addition).
+    //  * every build whose field products are real calls (CallOps) and G2: a load in flight cannot cross a CALL --
+    //    its scoreboard is waited for first, which exposed the whole DRAM latency of a table gather once per addition
+    //    (ncu, full digit tables: long_scoreboard 0.59 per issue) -- and G2 has no registers for a second point
+    //    anyway.  These stage the point through SHARED MEMORY with cp.async (LDGSTS): issued before the addition,
+    //    waited for after it; it needs no destination registers, survives the calls, and unlike prefetch.global it is
+    //    never dropped on a TLB miss (the digit tables span > 100 GB).  One 16-byte slot column per thread,
+    //    [quad][thread], so the LDS.128 / LDGSTS.128 of a warp are conflict-free.
+    constexpr bool PREFETCH_TO_REGS = sizeof(F) == sizeof(Fq) && MIN_BLOCKS <= 3 && std::is_same<O, InlineOps>::value;
+    constexpr int Q = sizeof(Affine<F>) / 16;
+    __shared__ uint4 stage[PREFETCH_TO_REGS ? 1 : Q * 128];
+    uint4* my_stage = stage + (PREFETCH_TO_REGS ? 0 : threadIdx.x);
+    auto stage_issue = [&](const Affine<F>* p) {
+        const uint4* src = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(my_stage + q * 128);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + q));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    auto stage_take = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        Affine<F> r;
+        uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < Q; q++) dst[q] = my_stage[q * 128];
+        return r;
+    };
     uint32_t v = sorted[k];
-    Affine<F> cur = load_affine(base_ptr(v));
+    Affine<F> cur;
+    if constexpr (PREFETCH_TO_REGS) {
+        cur = load_affine(base_ptr(v));
+    } else {
+        stage_issue(base_ptr(v));
+        cur = stage_take();
+    }
     bool neg = (v >> 31) != 0;
-    // G1: the next point is loaded into registers while the current addition runs.  G2: accumulator (96
-    // registers) + current point (48) + a second point (48) do not fit in 255 registers next to the formula's
-    // temporaries (ncu: 1.4 GB of local-memory spill traffic per launch), so the next point is only prefetched
-    // into L1 and loaded after the addition.
-    constexpr bool PREFETCH_TO_REGS = sizeof(F) == sizeof(Fq) && MIN_BLOCKS <= 3;
     for (;;) {
         const uint32_t kn = k + 1;
         Affine<F> nxt;
         uint32_t vn = 0;
         if (kn < end) {
             vn = sorted[kn];
-            const Affine<F>* np = base_ptr(vn);
-            if constexpr (PREFETCH_TO_REGS) {
-                nxt = load_affine(np);  // in flight during the add
-            } else {
-#pragma unroll
-                for (int off = 0; off < (int)sizeof(Affine<F>); off += 128)
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(np) + off));
-            }
+            if constexpr (PREFETCH_TO_REGS) nxt = load_affine(base_ptr(vn));  // in flight during the addition
+            else stage_issue(base_ptr(vn));
         }
         ec_madd<F, O>(acc, cur, neg);
         if (kn >= end) break;
@@ -379,7 +407,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
             } while (bend == kn);
         }
         if constexpr (PREFETCH_TO_REGS) cur = nxt;
-        else cur = load_affine(base_ptr(vn));
+        else cur = stage_take();
         neg = (vn >> 31) != 0;
         k = kn;
     }
@@ -665,7 +693,7 @@ __global__ void __launch_bounds__(32) points_sum_kernel(const Affine<F>* __restr
 }
 
 // ---------------------------------------------------------------- full digit tables (precompute level 2)
-// With T[(w n + i) mult + m] = (m + 1) 2^(c w) P_i resident, sum_i k_i P_i = sum over the non-zero signed digits
+// With T[(i W + w) mult + m] = (m + 1) 2^(c w) P_i resident, sum_i k_i P_i = sum over the non-zero signed digits
 // d of every scalar of  sign(d) * T[w, i, |d| - 1]: one mixed addition per digit, the same count as the bucket
 // method's accumulation, and NOTHING else -- no sort (the entries are taken in scalar order), no fold of split
 // buckets, no bucket reduction, no window combine.  The entry list of a batch is laid out proof after proof and cut
@@ -703,7 +731,7 @@ __global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, 
         const int32_t d = next_digit(k, w, c, carry);
         if (d == 0) continue;
         const uint32_t m = (uint32_t)(d < 0 ? -d : d) - 1;
-        entries[pos++] = (uint32_t)(((size_t)w * n + i) * mult + m) | (d < 0 ? 0x80000000u : 0u);
+        entries[pos++] = (uint32_t)((i * windows + w) * mult + m) | (d < 0 ? 0x80000000u : 0u);
     }
 }
 
@@ -743,13 +771,16 @@ __global__ void __launch_bounds__(128) msm_sum_partials(const uint32_t* __restri
     if (t == 0) out[key] = acc;
 }
 
-// table build, step 1: row r = (w, i) of the window-multiple table Q -> its first `mult` multiples as XYZZ
+// table build, step 1: table row r = i * windows + w (base-major: the ~22 rows one scalar touches are adjacent, 4 MB
+// apart at most, so consecutive entries of a run mostly share a 2 MB page -- with the window-major order of Q they
+// were n rows = 1 GB apart and every gather was a TLB miss) <- the first `mult` multiples of Q[w * n + i], as XYZZ
 template <class F>
-__global__ void __launch_bounds__(64) table_multiples(const Affine<F>* __restrict__ Q, size_t rows, uint32_t mult,
-                                                      XYZZ<F>* __restrict__ out) {
+__global__ void __launch_bounds__(64) table_multiples(const Affine<F>* __restrict__ Q, size_t n, uint32_t windows, size_t r0,
+                                                      size_t rows, uint32_t mult, XYZZ<F>* __restrict__ out) {
     size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (r >= rows) return;
-    const Affine<F> q = load_affine(Q + r);
+    const size_t i = (r0 + r) / windows, w = (r0 + r) % windows;
+    const Affine<F> q = load_affine(Q + w * n + i);
     XYZZ<F> acc = XYZZ<F>::inf();
     XYZZ<F>* dst = out + r * mult;
     for (uint32_t m = 0; m < mult; m++) {
@@ -1161,7 +1192,7 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
         int rc = B200ZK_OK;
         for (size_t r0 = 0; r0 < rows && rc == B200ZK_OK; r0 += slab_rows) {
             const size_t nr = std::min(slab_rows, rows - r0), cnt = nr * mult;
-            table_multiples<F><<<div_up(nr, 64), 64, 0, ctx->stream>>>(Q + r0, nr, mult, (XYZZ<F>*)d_x);
+            table_multiples<F><<<div_up(nr, 64), 64, 0, ctx->stream>>>(Q, n, pl.windows, r0, nr, mult, (XYZZ<F>*)d_x);
             rc = check_launch(ctx, "table_multiples");
             if (rc != B200ZK_OK) break;
             table_to_affine<F><<<div_up(div_up(cnt, TA_CHUNK), 64), 64, 0, ctx->stream>>>((const XYZZ<F>*)d_x, cnt,

@@ -13,7 +13,7 @@ struct b200zk_bases {
     uint8_t* d_skip = nullptr;  // n flags: base i is the point at infinity (its digits never enter a bucket);
                                 // null when no base is (proving-key b queries are ~30 % infinity)
     size_t n_skip = 0;
-    // precompute level 2: the FULL digit table T[(w * n + i) * mult + m] = (m + 1) * 2^(c w) * P_i, m < mult = 2^(c-1),
+    // precompute level 2: the FULL digit table T[(i * windows + w) * mult + m] = (m + 1) * 2^(c w) * P_i, m < mult = 2^(c-1),
     // affine, resident in HBM (tens of GB per query: sized for the 180 GB of a B200).  An MSM over it is a plain sum
     // of one table entry per non-zero signed digit: no buckets, no sort, no bucket reduction.
     void* d_table = nullptr;
