@@ -555,7 +555,10 @@ def run_b200(args):
     if args.timeline and rank == 0:
         # one step with concurrency ON and every kernel family bracketed: shows the overlap of the streams
         ctx.prof_enable(True); ctx.prof_reset()
-        step_resident(0)
+        if args.no_pipeline:
+            step_resident(0)
+        else:
+            timed_pipeline(False, 4)               # four steps, two in flight: shows what overlaps across batches
         rows = ctx.prof_timeline()
         ctx.prof_enable(False)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -248,6 +248,7 @@ int b200zk_msm_sharded(b200zk_ctx* ctx, const b200zk_bases* h_local, const void*
                        size_t n_local, uint8_t* out_affine, uint8_t* out_is_inf) {
     if (!ctx || !h_local || !out_affine) return B200ZK_ERR_BAD_ARG;
     const size_t pt = h_local->group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     void* dout;
     B200ZK_TRY(scratch(ctx, "comm_msm_out", pt, &dout));
     B200ZK_TRY(msm_sharded_run(ctx, h_local, scalars_local, scalars_on_device, n_local, dout));

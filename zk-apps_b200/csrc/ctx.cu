@@ -67,6 +67,7 @@ int b200zk_init(int device, b200zk_ctx** out) {
 int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return B200ZK_ERR_BAD_ARG;
     if (strcmp(name, "concurrency") == 0) {
+        cudaSetDevice(ctx->device);
         cudaDeviceSynchronize();
         ctx->concurrency = value != 0;
         return B200ZK_OK;
@@ -129,6 +130,7 @@ const char* b200zk_last_error(b200zk_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int b200zk_sync(b200zk_ctx* ctx) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     for (int l = 0; l < b200zk_ctx::LANES; l++) B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->main_lane[l]));
     return B200ZK_OK;
 }
@@ -154,6 +156,7 @@ int b200zk_dev_free(b200zk_ctx* ctx, void* dptr) {
 
 int b200zk_dev_upload(b200zk_ctx* ctx, void* dptr, const void* host, size_t bytes) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;
@@ -161,6 +164,7 @@ int b200zk_dev_upload(b200zk_ctx* ctx, void* dptr, const void* host, size_t byte
 
 int b200zk_dev_download(b200zk_ctx* ctx, void* host, const void* dptr, size_t bytes) {
     if (!ctx) return B200ZK_ERR_BAD_ARG;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     B200ZK_CUDA(ctx, cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     B200ZK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return B200ZK_OK;

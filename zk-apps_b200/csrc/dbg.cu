@@ -87,20 +87,25 @@ __global__ void peak_imad32(uint32_t* out, uint32_t x, uint32_t y) {
     if (s == 0x12345678u) out[0] = s;
 }
 
+// 16 INDEPENDENT accumulator chains per thread; the multiplicands are loop constants, so the only dependence is the
+// addend (and the carry) of each chain -- the shape of a Montgomery row.  (The round-1 version fed the low word of the
+// accumulator back as a multiplicand: a longer dependence than any field product has, and it measured 7.3 T/s, below
+// the 9.1 T/s the Fq product itself sustains.)
 __global__ void peak_imad_wide(uint64_t* out, uint32_t x) {
-    uint64_t a[8];
+    uint64_t a[16];
+    uint32_t m[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = threadIdx.x + k;
-    for (int it = 0; it < PEAK_ITERS; it++) {
+    for (int k = 0; k < 16; k++) {
+        a[k] = threadIdx.x + k;
+        m[k] = x + 2 * k + 1;
+    }
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t lo = (uint32_t)a[k];
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(lo), "r"(x));
-        }
+        for (int k = 0; k < 16; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(m[k]), "r"(x));
     }
     uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) s ^= a[k];
+    for (int k = 0; k < 16; k++) s ^= a[k];
     if (s == 0x12345678ull) out[0] = s;
 }
 
@@ -422,6 +427,7 @@ int b200zk_fixed_base_mul(b200zk_ctx* ctx, int group, const uint8_t* scalars, si
     if (!ctx || !scalars || !out_points) return B200ZK_ERR_BAD_ARG;
     if (group != 1 && group != 2) return fail(ctx, B200ZK_ERR_BAD_ARG, "group must be 1 or 2");
     if (n == 0) return B200ZK_OK;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t pt = group == 1 ? sizeof(G1Affine) : sizeof(G2Affine);
     void *ds, *dout;
     B200ZK_TRY(scratch(ctx, "fb_s", n * 32, &ds));

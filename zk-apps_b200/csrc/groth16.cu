@@ -674,6 +674,7 @@ int b200zk_pk_export_query(b200zk_ctx* ctx, const b200zk_pk* pk, int which, uint
     const b200zk_bases* h = which == 0 ? &pk->a_query : which == 1 ? &pk->b_g1_query : which == 2 ? &pk->b_g2_query
                             : which == 3 ? &pk->l_query : &pk->h_query;
     if (count) *count = h->n;
+    B200ZK_CUDA(ctx, cudaSetDevice(ctx->device));
     if (out) B200ZK_CUDA(ctx, cudaMemcpy(out, h->d_points, h->n * (h->group == 1 ? 96 : 192), cudaMemcpyDeviceToHost));
     return B200ZK_OK;
 }
