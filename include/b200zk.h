@@ -115,7 +115,8 @@ int b200zk_dbg_field_op(b200zk_ctx* ctx, int field, int op, const uint8_t* a, co
 /* Integer-pipe micro-benchmarks: kind 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (mad.wide), 2 = Fr
  * Montgomery mul, 3 = Fq Montgomery mul, 4 = DFMA, 5 = Fq Montgomery mul on the FP64 pipe (experiment),
  * 6 = one integer and one FP64 product chain per thread, 7 = integer products in the even warps and FP64
- * products in the odd warps of every CTA.  Returns operations (IMADs, or field muls) per
+ * products in the odd warps of every CTA, 8 = carry-chained wide multiply-adds (the rows of a Montgomery product,
+ * four independent accumulators per thread), 9 = two independent Fq product chains per thread.  Returns operations (IMADs, or field muls) per
  * second sustained over all SMs -- the measured denominator of the integer roofline. */
 int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec);
 /* Groundwork (csrc/ec_batch_affine.cuh): out[i] = p[i] + q[i] for n pairs of affine points (host buffers, FFI

@@ -15,7 +15,7 @@ n = 1 << 10
 for group in (1, 2):
     pts = ctx.fixed_base_mul(group, util.rand_fr_bytes_fast(1, n))
     ss = util.rand_fr_bytes_fast(2, n).copy()
-    ss[:32 * 100] = ss[:32]                                   # 100 equal scalars: one big bucket
+    ss[:32 * 100] = np.tile(ss[:32], 100)                     # 100 equal scalars: one big bucket
     want, _ = z.VariableBaseMSM.msm_bigint(ctx, group, pts, ss)
     ctx.set_option("msm_glv", 0)
     assert z.VariableBaseMSM.msm_bigint(ctx, group, pts, ss)[0] == want

@@ -5,6 +5,7 @@
 #include "ec.cuh"
 #include "field_dfma.cuh"
 #include "ec_batch_affine.cuh"
+#include "fq28.cuh"
 
 using namespace b200zk;
 
@@ -100,13 +101,73 @@ __global__ void peak_imad_wide(uint64_t* out, uint32_t x) {
         m[k] = x + 2 * k + 1;
     }
     for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        // the second factor changes every iteration: with a loop-invariant product ptxas hoists the multiplication and
+        // the loop degenerates into 64-bit additions (that is what the first version of this kernel measured)
+        const uint32_t y = x + 0x9e3779b9u * (uint32_t)it;
 #pragma unroll
-        for (int k = 0; k < 16; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(m[k]), "r"(x));
+        for (int k = 0; k < 16; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[k]) : "r"(m[k]), "r"(y));
     }
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) s ^= a[k];
     if (s == 0x12345678ull) out[0] = s;
+}
+
+// carry-CHAINED wide multiply-adds (mad.lo.cc / madc.hi.cc rows as the Montgomery product issues them = IMAD.WIDE.U32
+// with carry out and IMAD.WIDE.U32.X with carry in), four independent accumulators per thread: is the chained form
+// issued at the rate of the plain IMAD.WIDE, or is the carry what halves the field product's multiplier use?
+__global__ void peak_imad_wide_carry(uint32_t* out, const uint32_t* in) {
+    uint32_t X[4][13], a[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) a[k] = in[k] + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 13; k++) X[c][k] = threadIdx.x + c + k;
+#if defined(__CUDA_ARCH__)
+    for (int it = 0; it < PEAK_ITERS / 4; it++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) ptx::row_even<12>(X[c], a, a[c] + it);   // 6 chained wide multiply-adds each
+    }
+#endif
+    uint32_t s = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int k = 0; k < 13; k++) s ^= X[c][k];
+    if (s == 0x12345678u) out[0] = s;
+}
+
+// two INDEPENDENT Fq product chains per thread in one instruction stream (what interleaving two additions, or the
+// two halves of an Fq2 product, would give the scheduler)
+__global__ void peak_fqmul_ilp2(Fq* out, const Fq* in) {
+    Fq a = in[0], b = in[1], c = in[1], d = in[0];
+    a.v[0] ^= threadIdx.x;
+    c.v[1] ^= threadIdx.x;
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        a = fp_mul(a, b);
+        c = fp_mul(c, d);
+        b = fp_mul(b, a);
+        d = fp_mul(d, c);
+    }
+    if (a.v[0] == 0x12345678u && b.v[1] == 0x9abcdef0u && c.v[2] == 1u && d.v[3] == 2u) out[0] = a;
+}
+
+// back-to-back Fq products in reduced radix (fq28.cuh: 14 x 28-bit limbs, carry-free IMAD.WIDE columns)
+__global__ void peak_fq28mul(r28::Fq28* out, const uint32_t* in) {
+    r28::Fq28 a, b;
+#pragma unroll
+    for (int k = 0; k < r28::NL; k++) {
+        a.l[k] = (in[k] + threadIdx.x) & r28::LM;
+        b.l[k] = (in[k + 1] + 3 * threadIdx.x) & r28::LM;
+    }
+    a.l[r28::NL - 1] &= 0xffff;
+    b.l[r28::NL - 1] &= 0xffff;
+    for (int it = 0; it < PEAK_ITERS / 2; it++) {
+        a = r28::mul(a, b);
+        b = r28::mul(b, a);
+    }
+    if (a.l[0] == 0x02345678u && b.l[1] == 0x0abcdef0u) out[0] = a;
 }
 
 __global__ void peak_dfma(double* out, double x, double y) {
@@ -354,7 +415,7 @@ int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {
     twor[0] = Fr::one();
     twor[1] = fp_add(Fr::one(), Fr::one());
     if (kind == 2) B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, twor, sizeof(twor), cudaMemcpyHostToDevice, ctx->stream));
-    if (kind == 3 || kind == 5 || kind == 6 || kind == 7)
+    if (kind == 3 || kind == 5 || kind == 6 || kind == 7 || kind == 8 || kind == 9 || kind == 10)
         B200ZK_CUDA(ctx, cudaMemcpyAsync(dbuf, two, sizeof(two), cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
     const int blocks = ctx->sm_count * 8;
@@ -396,6 +457,18 @@ int b200zk_dbg_int_peak(b200zk_ctx* ctx, int kind, double* ops_per_sec) {
                 break;
             case 7:
                 peak_fqmul_split<<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = PEAK_ITERS;
+                break;
+            case 8:
+                peak_imad_wide_carry<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)dbuf + 512, (const uint32_t*)dbuf);
+                ops = 6.0 * PEAK_ITERS;          // 4 rows of 6 wide multiply-adds per iteration, PEAK_ITERS / 4 iterations
+                break;
+            case 9:
+                peak_fqmul_ilp2<<<blocks, threads, 0, ctx->stream>>>((Fq*)dbuf + 16, (const Fq*)dbuf);
+                ops = 2.0 * PEAK_ITERS;
+                break;
+            case 10:
+                peak_fq28mul<<<blocks, threads, 0, ctx->stream>>>((r28::Fq28*)((uint32_t*)dbuf + 512), (const uint32_t*)dbuf);
                 ops = PEAK_ITERS;
                 break;
             default: return fail(ctx, B200ZK_ERR_BAD_ARG, "unknown kind");
