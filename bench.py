@@ -460,7 +460,7 @@ def run_b200(args):
     hbm_peak, peak_src = load_peaks()
     B = args.batch
     relation = z.UpdateNoteRelation(z.WITHDRAW, TREE_HEIGHT)
-    # precompute level 2 = full digit tables of every query resident in HBM (~135 GB of the 180): the MSMs of a proof
+    # precompute level 2 = full digit tables of every query resident in HBM (147 GiB of the 179): the MSMs of a proof
     # are then plain sums of table entries (include/b200zk.h); level 1 = window multiples + bucket method
     if args.table_c_g1:
         ctx.set_option("table_c_g1", args.table_c_g1)
@@ -698,9 +698,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="time the synchronous calls (one batch in flight)")
     ap.add_argument("--table-c-g1", type=int, default=0, help="window of the G1 digit tables (0 = library default 12)")
-    ap.add_argument("--table-c-g2", type=int, default=0, help="window of the G2 digit table (0 = library default 11)")
+    ap.add_argument("--table-c-g2", type=int, default=0, help="window of the G2 digit table (0 = library default 12)")
     ap.add_argument("--precompute", type=int, default=2, help="proving-key residency: 1 = window multiples (bucket method), "
-                                                                 "2 = full digit tables (~135 GB)")
+                                                                 "2 = full digit tables (147 GiB)")
     ap.add_argument("--timeline", default="", help="write a per-kernel timeline of one concurrent step to gpurun_out/<name>")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -73,7 +73,7 @@ int b200zk_sync(b200zk_ctx* ctx);
  * streams; 0 serialises everything on the ctx stream (used for per-kernel profiling).
  * "msm_parts" (default 0 = automatic: 4 from 2^23 points, else 1): number of window groups a single
  * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream.
- * "table_c_g1" (default 12) / "table_c_g2" (default 11): window of full digit tables (precompute level 2) built after
+ * "table_c_g1" (default 12) / "table_c_g2" (default 12): window of full digit tables (precompute level 2) built after
  * the call.
  * "msm_glv" (default 1): MSMs (G1 and G2) over plain bases split every scalar as k1 + k2*lambda (two non-negative
  * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way FOR BASES
@@ -174,7 +174,7 @@ int b200zk_msm_g2(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flag
  * (memory x windows; all windows then share one bucket set and nothing is left to combine); 2 = the FULL DIGIT TABLE
  * (m + 1) 2^(c w) P_i for every m < 2^(c-1), resident in HBM (n * ceil(256/c) * 2^(c-1) points: 24 GB for a G1 query
  * of 5,653 points at c = 12 -- sized for the 180 GB of a B200; window from the options "table_c_g1" (default 12) /
- * "table_c_g2" (default 11) at the time of this call).  An MSM over a full table is one mixed addition per non-zero
+ * "table_c_g2" (default 12) at the time of this call).  An MSM over a full table is one mixed addition per non-zero
  * signed digit and nothing else: no buckets, no sort, no bucket reduction.  Same result bytes at every level. */
 int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8_t* inf_flags,
                         size_t n, int precompute, b200zk_bases** out);
@@ -312,7 +312,7 @@ int b200zk_merkle_fill_update_note_inputs_device(b200zk_ctx* ctx, const b200zk_m
  * 5 x 32 B canonical LE) -- ark_groth16::generate_parameters_with_qap [recall]; fixed-base
  * multiplications run on the GPU.  vk_out (may be NULL): alpha_g1 (96) | beta_g2 (192) |
  * gamma_g2 (192) | delta_g2 (192) | gamma_abc_g1 (num_inputs * 96).
- * precompute: 0 / 1 / 2 as in b200zk_bases_upload, applied to every query (2 = full digit tables: ~135 GB for the
+ * precompute: 0 / 1 / 2 as in b200zk_bases_upload, applied to every query (2 = full digit tables: ~158 GB (147 GiB) for the
  * withdraw key at the default windows, built once in a few seconds).
  * b200zk_groth16_prove_batch = create_proof_with_reduction(circuit, pk, r, s) for `batch` full
  * assignments (batch*num_vars*32 B Montgomery, host or device); r, s: batch*32 B canonical LE.

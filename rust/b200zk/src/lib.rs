@@ -160,6 +160,58 @@ impl Gpu {
     }
 }
 
+/// Device-resident bases of one rank's slice of a large MSM (`b200zk_bases_upload`, plain bases).
+pub struct GpuBasesG1<'a> {
+    gpu: &'a Gpu,
+    raw: *mut sys::b200zk_bases,
+    n: usize,
+}
+
+impl Drop for GpuBasesG1<'_> {
+    fn drop(&mut self) {
+        unsafe { sys::b200zk_bases_free(self.gpu.ctx, self.raw) }
+    }
+}
+
+impl Gpu {
+    /// The 128-byte NCCL id rank 0 creates and hands to the other ranks (any transport of the host's choosing).
+    pub fn comm_unique_id() -> Result<[u8; 128], Error> {
+        let mut id = [0u8; 128];
+        let rc = unsafe { sys::b200zk_comm_unique_id(id.as_mut_ptr()) };
+        if rc != sys::B200ZK_OK {
+            return Err(Error { code: rc, message: "NCCL not loadable (libnccl.so.2)".into() });
+        }
+        Ok(id)
+    }
+
+    /// Collective over all ranks: attaches an NCCL communicator to this context (`ncclCommInitRank`).
+    pub fn comm_init(&self, id: &[u8; 128], rank: i32, world: i32) -> Result<(), Error> {
+        self.check(unsafe { sys::b200zk_comm_init(self.ctx, id.as_ptr(), rank, world) })
+    }
+
+    /// This rank's contiguous slice of the bases of a sharded MSM, uploaded once.
+    pub fn upload_bases_g1(&self, bases: &[G1Affine]) -> Result<GpuBasesG1<'_>, Error> {
+        let (b, inf) = pack_g1(bases);
+        let mut raw = core::ptr::null_mut();
+        self.check(unsafe { sys::b200zk_bases_upload(self.ctx, 1, b.as_ptr(), inf.as_ptr(), bases.len(), 0, &mut raw) })?;
+        Ok(GpuBasesG1 { gpu: self, raw, n: bases.len() })
+    }
+
+    /// `VariableBaseMSM::msm_bigint` over all GPUs of the communicator: every rank passes ITS slice of the scalars
+    /// (same range as its bases) and gets the same result: local bucket pipeline -> in-place all_gather of the
+    /// 96-byte affine partials -> sum, one stream of work inside the library.
+    pub fn msm_sharded_g1(&self, bases: &GpuBasesG1, scalars_local: &[BigInt<4>]) -> Result<G1Projective, Error> {
+        if scalars_local.len() > bases.n {
+            return Err(Error { code: sys::B200ZK_ERR_BAD_LEN, message: "more scalars than bases in this rank's slice".into() });
+        }
+        let (mut out, mut is_inf) = ([0u8; 96], 0u8);
+        self.check(unsafe {
+            sys::b200zk_msm_sharded(self.ctx, bases.raw, scalars_local.as_ptr() as *const _, 0, scalars_local.len(), out.as_mut_ptr(), &mut is_inf)
+        })?;
+        Ok(unpack_g1(&out, is_inf != 0).into())
+    }
+}
+
 impl Drop for Gpu {
     fn drop(&mut self) {
         unsafe { sys::b200zk_destroy(self.ctx) }
@@ -228,6 +280,43 @@ pub fn create_proofs(pk: &GpuProvingKey, inputs: &[Fr], batch: usize, r: &[Fr], 
         sys::B200ZK_OK => Ok(out.chunks(192).map(|c| Proof::deserialize_compressed(c).expect("proof bytes")).collect()),
         sys::B200ZK_ERR_UNSATISFIED => Err(SynthesisError::Unsatisfiable),
         _ => panic!("{:?}", pk.gpu.check(rc)),
+    }
+}
+
+/// A batch submitted with [`submit_proofs`]: `wait` blocks until the GPU is done and yields the proofs.  The output
+/// buffer lives inside the ticket, so the pointer the library keeps until the wait stays valid.
+pub struct PendingProofs<'a, 'b> {
+    pk: &'a GpuProvingKey<'b>,
+    ticket: u64,
+    out: Vec<u8>,
+}
+
+/// Asynchronous form of [`create_proofs`] (`b200zk_update_note_prove_submit`): returns without waiting for the GPU;
+/// up to two batches may be in flight per context, so that the witness generation of one batch and the assembly of
+/// the other run under bucket accumulation.  The input slices are free again on return.
+pub fn submit_proofs<'a, 'b>(pk: &'a GpuProvingKey<'b>, inputs: &[Fr], batch: usize, r: &[Fr], s: &[Fr]) -> Result<PendingProofs<'a, 'b>, Error> {
+    if r.len() != batch || s.len() != batch || inputs.len() != batch * (18 + 2 * pk.tree_height as usize) {
+        return Err(Error { code: sys::B200ZK_ERR_BAD_LEN, message: "inputs / r / s do not match the batch size".into() });
+    }
+    let (rb, sb) = (bigint_bytes(r), bigint_bytes(s));
+    let mut out = vec![0u8; batch * 192];
+    let mut ticket = 0u64;
+    pk.gpu.check(unsafe {
+        sys::b200zk_update_note_prove_submit(
+            pk.gpu.ctx, pk.raw, inputs.as_ptr() as *const _, 0, batch, rb.as_ptr(), sb.as_ptr(), out.as_mut_ptr(),
+            core::ptr::null_mut(), &mut ticket,
+        )
+    })?;
+    Ok(PendingProofs { pk, ticket, out })
+}
+
+impl PendingProofs<'_, '_> {
+    pub fn wait(self) -> Result<Vec<Proof<Bls12_381>>, SynthesisError> {
+        match unsafe { sys::b200zk_prove_wait(self.pk.gpu.ctx, self.ticket) } {
+            sys::B200ZK_OK => Ok(self.out.chunks(192).map(|c| Proof::deserialize_compressed(c).expect("proof bytes")).collect()),
+            sys::B200ZK_ERR_UNSATISFIED => Err(SynthesisError::Unsatisfiable),
+            rc => panic!("{:?}", self.pk.gpu.check(rc)),
+        }
     }
 }
 

@@ -195,7 +195,7 @@ def test_full_digit_table_msm(ctx, group, n, c):
     want, want_inf = plain.msm(ss.reshape(-1), n=n, batch=batch)
     ctx.set_option("table_c_g1" if group == 1 else "table_c_g2", c)
     full = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=2)
-    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 11)
+    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 12)
     got, got_inf = full.msm(ss.reshape(-1), n=n, batch=batch)
     assert bytes(got) == bytes(want) and list(got_inf) == list(want_inf) and got_inf[2] == 1
     one, _ = full.msm(ss[1].reshape(-1), n=n)                        # batch of one, host scalars

@@ -48,7 +48,7 @@ struct b200zk_ctx {
     bool concurrency = true;                               // b200zk_set_option("concurrency")
     int msm_parts = 0;                                     // b200zk_set_option("msm_parts"): 0 = automatic
     bool msm_glv = true;                                   // b200zk_set_option("msm_glv"): GLV for plain G1 bases
-    int table_c_g1 = 12, table_c_g2 = 11;                  // window of a full digit table (precompute level 2): the table
+    int table_c_g1 = 12, table_c_g2 = 12;                  // window of a full digit table (precompute level 2): the table
                                                            // holds n * ceil(256 / c) * 2^(c-1) points
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <memory>
 
+#include "glv.cuh"
 #include "types.cuh"
 
 using namespace b200zk;
@@ -177,6 +178,30 @@ __global__ void __launch_bounds__(32) fin_scalars(const DeltaTable* __restrict__
     }
 }
 
+// k * P for P in G1 with the GLV endomorphism and Shamir's trick: k = k1 + k2 * lambda (glv.cuh), phi(P) = (beta X, Y, ZZ,
+// ZZZ), one shared chain of 129 doublings with an addition of P, phi(P) or P + phi(P) where either bit is set:
+// ~129 D + ~97 A instead of ~255 D + ~128 A.  This scalar multiplication is the longest latency chain of a single
+// proof (one thread; nothing to overlap with once the MSMs are done).
+__device__ G1XYZZ g1_mul_glv(const G1XYZZ& P, const uint32_t* k) {
+    uint32_t k1[GLV_LIMBS], k2[GLV_LIMBS];
+    glv_split(k, k1, k2);
+    G1XYZZ Q = P;
+    Q.x = glv_phi_x(P.x);
+    G1XYZZ R = P;
+    ec_add<Fq, CallOps>(R, Q);
+    G1XYZZ acc = G1XYZZ::inf();
+    bool started = false;
+    for (int bit = 32 * GLV_LIMBS - 1; bit >= 0; bit--) {
+        if (started) acc = ec_dbl(acc);
+        const uint32_t b = ((k1[bit >> 5] >> (bit & 31)) & 1u) | (((k2[bit >> 5] >> (bit & 31)) & 1u) << 1);
+        if (b) {
+            ec_add<Fq, CallOps>(acc, b == 1 ? P : b == 2 ? Q : R);
+            started = true;
+        }
+    }
+    return acc;
+}
+
 // msm_g1 layout: [4][batch] = a, b_g1, l, h.
 // fin_g1_mul: which = 0 (needs msm a):   u_g1[0] = s * A,   A  = alpha + msm_a  + r*delta1
 //             which = 1 (needs msm b_g1): u_g1[1] = r * B1,  B1 = beta1 + msm_b1 + s*delta1
@@ -191,7 +216,7 @@ __global__ void __launch_bounds__(32) fin_g1_mul(const Singles* __restrict__ sg,
     G1XYZZ P = t_g1[(size_t)which * batch + b];
     ec_madd(P, which == 0 ? sg->alpha_g1 : sg->beta_g1);
     ec_madd(P, msm_g1[(size_t)which * batch + b]);
-    u_g1[(size_t)which * batch + b] = ec_mul_scalar(P, k);
+    u_g1[(size_t)which * batch + b] = g1_mul_glv(P, k);
 }
 
 // canonical big-endian bytes of an Fq (48 B)

@@ -895,6 +895,11 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     uint32_t log_tl = 6;
     while (log_tl < 10 && (max_entries / n_keys) >= (4ull << log_tl)) log_tl++;
     while (log_tl > 3 && (max_entries >> log_tl) < 65536) log_tl--;
+    // full digit tables: every run of a proof leaves one partial for msm_sum_partials (one CTA per proof); a small batch
+    // must not be cut into so many runs that summing them becomes the latency of the MSM (one proof in 8-entry runs:
+    // 15,000 partials, 1.2 ms on one CTA)
+    if (pl.table)
+        while (log_tl < 10 && ((max_entries / n_keys) >> log_tl) > 4096) log_tl++;
     const uint32_t L0 = 1u << log_tl, L_min = L0 > 1 ? L0 / 2 : 1;   // msm_plan_runs picks L in [L0 / 2, 2 L0]
     const uint64_t max_runs = max_entries / L_min + 1;
     const uint64_t max_segs = (uint64_t)n_keys + max_runs + 1;

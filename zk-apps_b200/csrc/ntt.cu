@@ -45,8 +45,15 @@ struct PassParams {
     uint32_t lg[MAX_PASSES];  // log sizes of all passes (for the output digit reversal)
     uint32_t n_passes, pass;
     uint32_t inverse;
+    uint32_t async_load;   // tile loads as cp.async straight into the swizzled slots (B200ZK_NTT_ASYNC=0: through registers)
     uint64_t rows_total;   // last pass: batch * n / len
 };
+
+// 16 bytes global -> shared without passing through registers (LDGSTS); completion: cp.async.wait_all
+__device__ __forceinline__ void cp_async16(uint4* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
 
 __device__ __forceinline__ Fr load_fr(const Fr* p) {
     Fr r;
@@ -165,7 +172,35 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) ntt_pass_kernel(PassParams p) 
     }
 
     // ---- load (smem index = r * G + g)
-    if (!last) {
+    // Asynchronous-copy variant of the tile load (the nearest thing to the "TMA-staged tiles" of BASELINE.json that fits
+    // this layout: a tensor-map box cannot write the split, XOR-folded 16-byte planes the butterflies read conflict-free,
+    // and a linear tile would cost a second pass through shared memory).  Measured (profiles/r02_ntt_async.log): 0.5-1.7 %
+    // at 2^16...2^24 (2^22: 0.991 -> 0.986 ms) -- small, because with two CTAs per SM the loads of one tile already hide
+    // under the butterflies of the other, but consistent: on by default (B200ZK_NTT_ASYNC=0 restores the register path).
+    if (p.async_load && !p.pre_scale) {
+        for (uint32_t e = tid; e < tile; e += T) {
+            uint64_t addr;
+            uint32_t slot;
+            if (!last) {
+                const uint32_t g = e & (G - 1), r = e >> p.log_g;
+                addr = base + ((uint64_t)r << p.log_inner) + g;
+                slot = e;
+            } else {
+                const uint32_t r = e & (len - 1), g = e >> p.log_len;
+                const uint64_t row = row0 + g;
+                slot = r * G + g;
+                if (row >= p.rows_total) {
+                    sstore(d_lo, d_hi, slot, Fr::zero());
+                    continue;
+                }
+                addr = (row << p.log_len) + r;
+            }
+            const uint32_t sw = swz(slot);
+            cp_async16(d_lo + sw, reinterpret_cast<const uint4*>(p.in + addr));
+            cp_async16(d_hi + sw, reinterpret_cast<const uint4*>(p.in + addr) + 1);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    } else if (!last) {
         for (uint32_t e = tid; e < tile; e += T) {
             const uint32_t g = e & (G - 1), r = e >> p.log_g;
             const uint64_t addr = base + ((uint64_t)r << p.log_inner) + g;
@@ -403,6 +438,8 @@ int ntt_device(b200zk_ctx* ctx, Fr* d_data, uint32_t log_n, bool inverse, const 
         p.n_passes = P;
         p.pass = q;
         p.inverse = inverse ? 1 : 0;
+        static const int async_env = getenv("B200ZK_NTT_ASYNC") ? atoi(getenv("B200ZK_NTT_ASYNC")) : 1;
+        p.async_load = async_env ? 1u : 0u;
         const bool last = q + 1 == P;
         uint64_t tiles;
         if (!last) {
