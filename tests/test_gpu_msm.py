@@ -207,3 +207,53 @@ def test_full_digit_table_msm(ctx, group, n, c):
     few1, _ = win.msm(ss[3, :10].reshape(-1), n=10)
     assert bytes(few1) == bytes(ref)
     plain.free(); full.free(); win.free()
+
+
+@pytest.mark.parametrize("group,n,c,levels,b", [(1, 300, 5, 4, 32), (1, 77, 8, 3, 16), (1, 1000, 6, 1, 64), (2, 120, 4, 4, 32),
+                                                (2, 90, 5, 2, 16)])
+def test_digit_table_affine_levels(ctx, group, n, c, levels, b):
+    """Full digit tables with the batched-affine pairwise levels in front of the running sums (csrc/msm_affine.cuh):
+    same bytes as the bucket method over plain bases -- random batch incl. bases at infinity, zero / one / r - 1
+    scalars and an all-zero proof (entry lists padded to 2^levels per proof), then the special cases of the affine
+    addition on purpose: repeated bases with equal one-digit scalars (every pair of every level is a doubling),
+    P / -P pairs (sums to infinity at level 0, infinity + infinity above), and a mix."""
+    ks = util.rand_fr_bytes_fast(900 + n, n)
+    pts = ctx.fixed_base_mul(group, ks).copy()
+    pt = 96 if group == 1 else 192
+    pts[3 * pt:4 * pt] = 0
+    batch = 5
+    ss = util.rand_fr_bytes_fast(950 + n, batch * n).reshape(batch, n, 32).copy()
+    ss[0, 0] = 0; ss[0, 1] = np.frombuffer((1).to_bytes(32, "little"), dtype=np.uint8)
+    ss[0, 2] = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint8)
+    ss[2] = 0
+    ss[4, 1:] = 0                                                    # a proof with a single non-zero scalar
+    plain = z.VariableBaseMSM.Bases(ctx, group, pts)
+    want, want_inf = plain.msm(ss.reshape(-1), n=n, batch=batch)
+    opt = "table_c_g1" if group == 1 else "table_c_g2"
+    ctx.set_option(opt, c)
+    ctx.set_option("msm_affine_levels", levels); ctx.set_option("msm_affine_min_entries", 0); ctx.set_option("msm_affine_b", b)
+    try:
+        full = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=2)
+        got, got_inf = full.msm(ss.reshape(-1), n=n, batch=batch)
+        assert bytes(got) == bytes(want) and list(got_inf) == list(want_inf) and got_inf[2] == 1
+        full.free(); plain.free()
+        # ---- special cases: m copies of P (and of -P) with the same small scalar
+        cv, enc, dec, _ = CURVES[group]
+        P = cv.mul(cv.gen, 0xabcdef12345)
+        N = cv.neg(P)
+        m = 64
+        for name, seq, k_total in [("doublings", [P] * m, m), ("opposites", [P, N] * (m // 2), 0),
+                                   ("mixed", [P, P, N, N] * (m // 4) + [P] * 3, 3),
+                                   ("dbl-then-cancel", [P] * (m // 2) + [N] * (m // 2), 0)]:
+            arr = enc(seq)
+            h = z.VariableBaseMSM.Bases(ctx, group, arr, precompute=2)
+            for s in (1, 3, (1 << (c - 1)) - 1):
+                sc = util.scalars_array([s] * len(seq))
+                out, inf = h.msm(sc, n=len(seq))
+                res = dec(out)[0]
+                expect = cv.mul(P, k_total * s % R) if k_total else None
+                assert res == expect and bool(inf[0]) == (expect is None), (name, s)
+            h.free()
+    finally:
+        ctx.set_option(opt, 12)
+        ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 32)

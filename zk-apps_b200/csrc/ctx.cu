@@ -18,6 +18,13 @@ int b200zk_init(int device, b200zk_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return B200ZK_ERR_CUDA;
     b200zk_ctx* ctx = new b200zk_ctx();
     ctx->device = device;
+    // experiment / test overrides of the affine-level defaults (b200zk_set_option has the same knobs)
+    if (const char* e = getenv("B200ZK_AFFINE_LEVELS")) ctx->msm_affine_levels = std::max(0, std::min(8, atoi(e)));
+    if (const char* e = getenv("B200ZK_AFFINE_MIN_ENTRIES")) ctx->msm_affine_min_entries = std::max(0ll, atoll(e));
+    if (const char* e = getenv("B200ZK_AFFINE_B")) {
+        const int v = atoi(e);
+        if (v == 16 || v == 32 || v == 64) ctx->msm_affine_b = v;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     // Stream priorities order the work of a proof batch (numerically lower = more urgent): the assembly pieces
@@ -84,6 +91,21 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
     if (strcmp(name, "table_c_g1") == 0 || strcmp(name, "table_c_g2") == 0) {  // window of full digit tables built from now on
         if (value < 2 || value > 16) return fail(ctx, B200ZK_ERR_BAD_ARG, "table window must be 2..16");
         (name[9] == '1' ? ctx->table_c_g1 : ctx->table_c_g2) = value;
+        return B200ZK_OK;
+    }
+    if (strcmp(name, "msm_affine_levels") == 0) {  // rounds of batched-affine pairwise additions over digit tables; 0 = off
+        if (value < 0 || value > 8) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_levels must be 0..8");
+        ctx->msm_affine_levels = value;
+        return B200ZK_OK;
+    }
+    if (strcmp(name, "msm_affine_min_entries") == 0) {  // smaller batches keep the XYZZ running sums only
+        if (value < 0) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_min_entries must be >= 0");
+        ctx->msm_affine_min_entries = value;
+        return B200ZK_OK;
+    }
+    if (strcmp(name, "msm_affine_b") == 0) {  // additions per lane that share one inversion per warp
+        if (value != 16 && value != 32 && value != 64) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_b must be 16, 32 or 64");
+        ctx->msm_affine_b = value;
         return B200ZK_OK;
     }
     return fail(ctx, B200ZK_ERR_BAD_ARG, std::string("unknown option ") + name);

@@ -564,6 +564,180 @@ HD Fp<C> fp_inv_uniform(const Fp<C>& a) {
     return fp_mul(fp_mul(x2, Fp<C>::r2()), Fp<C>::r2());
 }
 
+// Inversion by "safegcd" division steps (Bernstein-Yang 2019) on 30-bit signed limbs, 30 steps at a time: the steps of
+// one batch run on the low words of f and g only and yield a 2x2 transition matrix t with |entries| <= 2^30; then
+// [f, g] <- t [f, g] / 2^30 (exact) and [d, e] <- t [d, e] / 2^30 (mod p) are 4 + 6 multiply-accumulate rows over the
+// limbs.  ~25 batches for a 381-bit modulus, ~18 k instructions with no long carry chain -- a quarter of the bit-by-bit
+// Euclid of fp_inv and far less dependent -- which is what makes one inversion per warp cheap enough for the batched-
+// affine additions (msm_affine.cuh).  Variable time (counts trailing zeros, stops when g = 0): operands are public, and
+// the caller runs it on warp-uniform data, so nothing diverges.  Invariants: d * a = f, e * a = g (mod p); at the end
+// g = 0, f = +-1, so +-d = a^-1.  Total on every N-limb word like fp_inv (reduces first; multiples of p give 0).
+// Pinned against pow(x, -1, p) on the host (tests/test_host.py::test_host_field_ops, op 9) and against fp_inv.
+template <class C>
+HD Fp<C> fp_inv_safegcd(const Fp<C>& a) {
+    constexpr int N = C::N;
+    constexpr int L = (32 * N + 2 + 29) / 30;  // 30-bit limbs: 13 for Fq, 9 for Fr (room for the range (-2p, p))
+    constexpr int32_t M30 = 0x3fffffff;
+    uint32_t w[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) w[i] = a.v[i];
+    for (;;) {  // canonicalise: at most 2^(32N) / p < 10 subtractions
+        uint32_t t[N];
+        uint64_t br = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            const uint64_t dd = (uint64_t)w[i] - C::mod(i) - br;
+            t[i] = (uint32_t)dd;
+            br = (dd >> 63) & 1;
+        }
+        if (br) break;
+#pragma unroll
+        for (int i = 0; i < N; i++) w[i] = t[i];
+    }
+    int32_t f[L], g[L], d[L], e[L], pm[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        const int bit = 30 * i, limb = bit >> 5, sh = bit & 31;
+        uint64_t vg = limb < N ? w[limb] : 0u, vp = limb < N ? C::mod(limb) : 0u;
+        if (limb + 1 < N) {
+            vg |= (uint64_t)w[limb + 1] << 32;
+            vp |= (uint64_t)C::mod(limb + 1) << 32;
+        }
+        g[i] = (int32_t)((vg >> sh) & M30);
+        pm[i] = (int32_t)((vp >> sh) & M30);
+        f[i] = pm[i];
+        d[i] = 0;
+        e[i] = 0;
+    }
+    e[0] = 1;
+    uint32_t pinv = C::mod(0);  // p^-1 mod 2^32 by Newton (p odd: p * p = 1 mod 8)
+#pragma unroll
+    for (int i = 0; i < 4; i++) pinv *= 2u - C::mod(0) * pinv;
+    int32_t eta = -1;
+    for (int it = 0; it < 48; it++) {  // ends on g = 0: <= ceil((49 * 384 + 57) / 17 / 30) = 38 batches
+        {
+            uint32_t o = 0;
+#pragma unroll
+            for (int i = 0; i < L; i++) o |= (uint32_t)g[i];
+            if (o == 0) break;
+        }
+        // ---- 30 division steps on the low words -> t = [u v; q r]
+        uint32_t u = 1, v = 0, q = 0, r = 1, ff = (uint32_t)f[0], gg = (uint32_t)g[0];
+        int i = 30;
+        for (;;) {
+            const uint32_t sentinel = gg | (0xffffffffu << i);
+#if defined(__CUDA_ARCH__)
+            const int zeros = __ffs((int)sentinel) - 1;
+#else
+            const int zeros = __builtin_ctz(sentinel);
+#endif
+            gg >>= zeros;
+            u <<= zeros;
+            v <<= zeros;
+            eta -= zeros;
+            i -= zeros;
+            if (i == 0) break;
+            uint32_t wm;
+            if (eta < 0) {  // swap: (f, g) <- (g, -f); cancel up to 6 low bits of g
+                eta = -eta;
+                uint32_t tmp = ff; ff = gg; gg = 0u - tmp;
+                tmp = u; u = q; q = 0u - tmp;
+                tmp = v; v = r; r = 0u - tmp;
+                const int limit = (eta + 1) > i ? i : (eta + 1);
+                const uint32_t m = (0xffffffffu >> (32 - limit)) & 63u;
+                wm = (ff * gg * (ff * ff - 2u)) & m;      // -g / f mod 2^6
+            } else {        // cancel up to 4 low bits
+                const int limit = (eta + 1) > i ? i : (eta + 1);
+                const uint32_t m = (0xffffffffu >> (32 - limit)) & 15u;
+                wm = ff + (((ff + 1u) & 4u) << 1);         // 1 / f mod 2^4
+                wm = ((0u - wm) * gg) & m;
+            }
+            gg += ff * wm;
+            q += u * wm;
+            r += v * wm;
+        }
+        const int32_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)r;
+        // ---- [d, e] <- t [d, e] / 2^30 mod p, kept in (-2p, p)
+        {
+            const int32_t sd = d[L - 1] >> 31, se = e[L - 1] >> 31;
+            int32_t md = (tu & sd) + (tv & se), me = (tq & sd) + (tr & se);
+            int64_t cd = (int64_t)tu * d[0] + (int64_t)tv * e[0];
+            int64_t ce = (int64_t)tq * d[0] + (int64_t)tr * e[0];
+            md -= (int32_t)((pinv * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+            me -= (int32_t)((pinv * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+            cd += (int64_t)pm[0] * md;
+            ce += (int64_t)pm[0] * me;
+            cd >>= 30;
+            ce >>= 30;
+#pragma unroll
+            for (int k = 1; k < L; k++) {
+                const int32_t dk = d[k], ek = e[k];
+                cd += (int64_t)tu * dk + (int64_t)tv * ek + (int64_t)pm[k] * md;
+                ce += (int64_t)tq * dk + (int64_t)tr * ek + (int64_t)pm[k] * me;
+                d[k - 1] = (int32_t)cd & M30;
+                e[k - 1] = (int32_t)ce & M30;
+                cd >>= 30;
+                ce >>= 30;
+            }
+            d[L - 1] = (int32_t)cd;
+            e[L - 1] = (int32_t)ce;
+        }
+        // ---- [f, g] <- t [f, g] / 2^30 (exact)
+        {
+            int64_t cf = (int64_t)tu * f[0] + (int64_t)tv * g[0];
+            int64_t cg = (int64_t)tq * f[0] + (int64_t)tr * g[0];
+            cf >>= 30;
+            cg >>= 30;
+#pragma unroll
+            for (int k = 1; k < L; k++) {
+                const int32_t fk = f[k], gk = g[k];
+                cf += (int64_t)tu * fk + (int64_t)tv * gk;
+                cg += (int64_t)tq * fk + (int64_t)tr * gk;
+                f[k - 1] = (int32_t)cf & M30;
+                g[k - 1] = (int32_t)cg & M30;
+                cf >>= 30;
+                cg >>= 30;
+            }
+            f[L - 1] = (int32_t)cf;
+            g[L - 1] = (int32_t)cg;
+        }
+    }
+    // ---- normalise d to [0, p), negated when f = -1
+    {
+        const int32_t sign = f[L - 1] >> 31;
+        int32_t cond_add = d[L - 1] >> 31;
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            d[k] += pm[k] & cond_add;
+            d[k] = (d[k] ^ sign) - sign;
+        }
+#pragma unroll
+        for (int k = 0; k < L - 1; k++) {
+            d[k + 1] += d[k] >> 30;
+            d[k] &= M30;
+        }
+        cond_add = d[L - 1] >> 31;
+#pragma unroll
+        for (int k = 0; k < L; k++) d[k] += pm[k] & cond_add;
+#pragma unroll
+        for (int k = 0; k < L - 1; k++) {
+            d[k + 1] += d[k] >> 30;
+            d[k] &= M30;
+        }
+    }
+    Fp<C> res;
+#pragma unroll
+    for (int i = 0; i < N; i++) {  // 30-bit limbs -> 32-bit words
+        const int bit = 32 * i, k = bit / 30, sh = bit % 30;
+        uint64_t acc = (uint64_t)(uint32_t)d[k] >> sh;
+        if (k + 1 < L) acc |= (uint64_t)(uint32_t)d[k + 1] << (30 - sh);
+        if (k + 2 < L) acc |= (uint64_t)(uint32_t)d[k + 2] << (60 - sh);
+        res.v[i] = (uint32_t)acc;
+    }
+    // (aR)^-1 = a^-1 R^-1; two Montgomery products by R^2 give a^-1 R
+    return fp_mul(fp_mul(res, Fp<C>::r2()), Fp<C>::r2());
+}
+
 using Fr = Fp<FrCfg>;
 using Fq = Fp<FqCfg>;
 

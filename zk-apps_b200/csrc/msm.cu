@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "glv.cuh"
+#include "msm_affine.cuh"
 #include "types.cuh"
 
 using namespace b200zk;
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         for (int q = 0; q < Q; q++) dst[q] = my_stage[q * 128];
         return r;
     };
-    uint32_t v = sorted[k];
+    // sorted == nullptr: the identity list (the points of an affine level are summed in array order)
+    uint32_t v = sorted ? sorted[k] : k;
     Affine<F> cur;
     if constexpr (PREFETCH_TO_REGS) {
         cur = load_affine(base_ptr(v));
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_accumulate(const Affine<F
         Affine<F> nxt;
         uint32_t vn = 0;
         if (kn < end) {
-            vn = sorted[kn];
+            vn = sorted ? sorted[kn] : kn;
             if constexpr (PREFETCH_TO_REGS) nxt = load_affine(base_ptr(vn));  // in flight during the addition
             else stage_issue(base_ptr(vn));
         }
@@ -717,16 +719,26 @@ __global__ void table_count(const uint32_t* scalars, size_t n, size_t stride, si
 }
 
 // entries of scalar (b, i) at off[b n + i]...: table index | sign
+// pstart (optional): padded first entry of every proof (table_pad_offsets); the list of proof b then lives at
+// pstart[b]... and the thread of its last scalar fills the gap up to pstart[b + 1] with AFF_PAD_ENTRY
 __global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, uint32_t c,
                               uint32_t windows, uint32_t mult, const uint8_t* __restrict__ skip,
-                              const uint32_t* __restrict__ off, uint32_t* __restrict__ entries) {
+                              const uint32_t* __restrict__ off, const uint32_t* __restrict__ pstart,
+                              uint32_t* __restrict__ entries) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     const size_t b = t / n, i = t % n;
+    uint32_t pos = off[t];
+    if (pstart) {
+        const uint32_t first = off[b * n];
+        pos = pos - first + pstart[b];
+        if (i == n - 1)
+            for (uint32_t q = pstart[b] + (off[(b + 1) * n] - first); q < pstart[b + 1]; q++) entries[q] = AFF_PAD_ENTRY;
+    }
     if (skip && skip[i]) return;
     uint32_t k[8];
     load_scalar(scalars, b * stride + i, mont != 0, k);
-    uint32_t carry = 0, pos = off[t];
+    uint32_t carry = 0;
     for (uint32_t w = 0; w < windows; w++) {
         const int32_t d = next_digit(k, w, c, carry);
         if (d == 0) continue;
@@ -739,6 +751,35 @@ __global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, 
 __global__ void table_proof_offsets(const uint32_t* __restrict__ off, size_t n, size_t batch, uint32_t* __restrict__ poff) {
     size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (b <= batch) poff[b] = off[b * n];
+}
+
+// Affine levels (msm_affine.cuh): every proof's entry list is padded to a multiple of 2^levels entries.
+// pstart[b] = padded first entry of proof b (pstart[batch] = padded total), poff_out[b] = pstart[b] >> levels = first
+// point of proof b after the last level.  One CTA, running carry over chunks of SCAN_THREADS proofs.
+__global__ void table_pad_offsets(const uint32_t* __restrict__ off, size_t n, size_t batch, uint32_t levels,
+                                  uint32_t* __restrict__ pstart, uint32_t* __restrict__ poff_out) {
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const uint32_t mask = (1u << levels) - 1;
+    for (size_t base = 0; base < batch; base += SCAN_THREADS) {
+        const size_t b = base + threadIdx.x;
+        const uint32_t len = b < batch ? (off[(b + 1) * n] - off[b * n] + mask) & ~mask : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(len, &total);
+        const uint32_t c = carry_s;
+        if (b < batch) {
+            pstart[b] = ex + c;
+            poff_out[b] = (ex + c) >> levels;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pstart[batch] = carry_s;
+        poff_out[batch] = carry_s >> levels;
+    }
 }
 
 // one CTA per proof: sum of the partial sums its runs left (or the single whole sum), log-depth
@@ -855,26 +896,76 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     B200ZK_TRY(scratch(ctx, "msm_counts", ((size_t)n_keys + 1) * 4, &d_counts, slot));
     B200ZK_TRY(scratch(ctx, "msm_offsets", ((size_t)n_keys + 1) * 4, &d_offsets, slot));
     B200ZK_TRY(scratch(ctx, "msm_cursor", ((size_t)n_keys + 1) * 4, &d_cursor, slot));
-    B200ZK_TRY(scratch(ctx, "msm_sorted", (size_t)max_entries * 4, &d_sorted, slot));
+    B200ZK_TRY(scratch(ctx, "msm_sorted", ((size_t)max_entries + (pl.table ? batch * 256 : 0)) * 4, &d_sorted, slot));   // + affine-level padding
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2",
                        (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets, slot));
 
     const size_t total = n * batch;
+    // ---- affine levels (msm_affine.cuh): K rounds of pairwise batched-affine additions before the XYZZ running sums
+    uint32_t aff_levels = 0;
+    if (pl.table && ctx->msm_affine_levels > 0 && max_entries >= (uint64_t)ctx->msm_affine_min_entries)
+        aff_levels = (uint32_t)ctx->msm_affine_levels;
+    const uint64_t padded_entries = max_entries + (aff_levels ? (uint64_t)batch << aff_levels : 0);
+    if (padded_entries >= (1ull << 32)) return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit entry offsets; split the batch");
+    const Affine<F>* acc_bases = (const Affine<F>*)(pl.table ? h->d_table : h->d_points);
+    const uint32_t* acc_entries = (const uint32_t*)d_sorted;
     if (pl.table) {
         // entries in scalar order, proof after proof: per-scalar digit counts -> scan -> entries; no sort, no atomics
-        ProfScope ps(ctx, "msm_sort", st);
-        void *d_cnt, *d_off;
-        B200ZK_TRY(scratch(ctx, "msm_tab_cnt", (total + 1) * 4, &d_cnt, slot));
-        B200ZK_TRY(scratch(ctx, "msm_tab_off", (total + 1) * 4, &d_off, slot));
-        table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, h->d_skip,
-                                                        (uint32_t*)d_cnt);
-        B200ZK_TRY(check_launch(ctx, "table_count"));
-        B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
-        table_entries<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, pl.mult,
-                                                          h->d_skip, (const uint32_t*)d_off, (uint32_t*)d_sorted);
-        B200ZK_TRY(check_launch(ctx, "table_entries"));
-        table_proof_offsets<<<div_up(batch + 1, 128), 128, 0, st>>>((const uint32_t*)d_off, n, batch, (uint32_t*)d_offsets);
-        B200ZK_TRY(check_launch(ctx, "table_proof_offsets"));
+        void *d_cnt, *d_off, *d_pstart = nullptr;
+        {
+            ProfScope ps(ctx, "msm_sort", st);
+            B200ZK_TRY(scratch(ctx, "msm_tab_cnt", (total + 1) * 4, &d_cnt, slot));
+            B200ZK_TRY(scratch(ctx, "msm_tab_off", (total + 1) * 4, &d_off, slot));
+            if (aff_levels) B200ZK_TRY(scratch(ctx, "msm_tab_pstart", (batch + 1) * 4, &d_pstart, slot));
+            table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, h->d_skip,
+                                                            (uint32_t*)d_cnt);
+            B200ZK_TRY(check_launch(ctx, "table_count"));
+            B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
+            if (aff_levels) {
+                table_pad_offsets<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)d_off, n, batch, aff_levels, (uint32_t*)d_pstart,
+                                                              (uint32_t*)d_offsets);
+                B200ZK_TRY(check_launch(ctx, "table_pad_offsets"));
+            } else {
+                table_proof_offsets<<<div_up(batch + 1, 128), 128, 0, st>>>((const uint32_t*)d_off, n, batch, (uint32_t*)d_offsets);
+                B200ZK_TRY(check_launch(ctx, "table_proof_offsets"));
+            }
+            table_entries<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, pl.mult,
+                                                              h->d_skip, (const uint32_t*)d_off, (const uint32_t*)d_pstart,
+                                                              (uint32_t*)d_sorted);
+            B200ZK_TRY(check_launch(ctx, "table_entries"));
+        }
+        if (aff_levels) {
+            // ping-pong: level 0 -> A (half the entries), level 1 -> B (a quarter), level 2 -> A, ...
+            ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_affine_g1" : "msm_affine_g2", st);
+            void *d_a, *d_b;
+            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_a_g1" : "msm_aff_a_g2",
+                               (size_t)(padded_entries / 2 + 1) * sizeof(Affine<F>), &d_a, slot));
+            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_b_g1" : "msm_aff_b_g2",
+                               (size_t)(padded_entries / 4 + 1) * sizeof(Affine<F>), &d_b, slot));
+            const uint32_t* d_total = (const uint32_t*)d_pstart + batch;
+            const int B = ctx->msm_affine_b;
+            const Affine<F>* src = (const Affine<F>*)h->d_table;
+            for (uint32_t lv = 0; lv < aff_levels; lv++) {
+                Affine<F>* dst = (Affine<F>*)((lv & 1) ? d_b : d_a);
+                const uint64_t max_pairs = padded_entries >> (lv + 1);
+                const unsigned grid = div_up(div_up(max_pairs, 32 * (size_t)B), 4);
+                constexpr int OCC = sizeof(F) == sizeof(Fq) ? 3 : 2;
+                auto kern = lv == 0 ? msm_affine_level<F, 32, true, OCC> : msm_affine_level<F, 32, false, OCC>;
+                if (B == 16) kern = lv == 0 ? msm_affine_level<F, 16, true, OCC> : msm_affine_level<F, 16, false, OCC>;
+                else if (B == 64) kern = lv == 0 ? msm_affine_level<F, 64, true, OCC> : msm_affine_level<F, 64, false, OCC>;
+                kern<<<grid, 128, 0, st>>>(src, lv == 0 ? (const uint32_t*)d_sorted : nullptr, d_total, lv, dst);
+                B200ZK_TRY(check_launch(ctx, "msm_affine_level"));
+                src = dst;
+            }
+            acc_bases = src;
+            acc_entries = nullptr;
+            if (ctx->prof_enabled && !ctx->concurrency) {  // work counter: additions done by the affine levels
+                uint32_t padded = 0;
+                B200ZK_CUDA(ctx, cudaMemcpyAsync(&padded, d_total, 4, cudaMemcpyDeviceToHost, st));
+                B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+                ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_affine_adds_g1" : "msm_affine_adds_g2"] += padded - (padded >> aff_levels);
+            }
+        }
     } else {
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
         ProfScope ps(ctx, "msm_sort", st);
@@ -892,16 +983,17 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     // ... and longer runs when the buckets are large (run ~ half the mean bucket), so that a bucket still
     // spans only ~3 runs: with 64-entry runs a 2^26-point GLV MSM (512 entries per bucket) sent every bucket,
     // 9 partials each, to the warp-per-bucket fold (129 ms instead of 6)
+    const uint64_t acc_max_entries = aff_levels ? padded_entries >> aff_levels : max_entries;   // what msm_accumulate sums
     uint32_t log_tl = 6;
-    while (log_tl < 10 && (max_entries / n_keys) >= (4ull << log_tl)) log_tl++;
-    while (log_tl > 3 && (max_entries >> log_tl) < 65536) log_tl--;
+    while (log_tl < 10 && (acc_max_entries / n_keys) >= (4ull << log_tl)) log_tl++;
+    while (log_tl > 3 && (acc_max_entries >> log_tl) < 65536) log_tl--;
     // full digit tables: every run of a proof leaves one partial for msm_sum_partials (one CTA per proof); a small batch
     // must not be cut into so many runs that summing them becomes the latency of the MSM (one proof in 8-entry runs:
     // 15,000 partials, 1.2 ms on one CTA)
     if (pl.table)
-        while (log_tl < 10 && ((max_entries / n_keys) >> log_tl) > 4096) log_tl++;
+        while (log_tl < 10 && ((acc_max_entries / n_keys) >> log_tl) > 4096) log_tl++;
     const uint32_t L0 = 1u << log_tl, L_min = L0 > 1 ? L0 / 2 : 1;   // msm_plan_runs picks L in [L0 / 2, 2 L0]
-    const uint64_t max_runs = max_entries / L_min + 1;
+    const uint64_t max_runs = acc_max_entries / L_min + 1;
     const uint64_t max_segs = (uint64_t)n_keys + max_runs + 1;
     // ---- which build of the accumulation kernel runs, and how many of its threads one wave holds
     // resident CTAs per SM (register cap 65536 / (128 * blocks)); tunable for experiments
@@ -959,8 +1051,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         static const int smem_kb = getenv("B200ZK_ACC_SMEM_KB") ? atoi(getenv("B200ZK_ACC_SMEM_KB")) : 0;
         if (smem_kb > 0) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
         kern<<<div_up(max_runs, acc_threads), acc_threads, (size_t)smem_kb * 1024, st>>>(
-            (const Affine<F>*)(pl.table ? h->d_table : h->d_points), d_phi, pl.glv ? (uint32_t)n : 0x80000000u,
-            (const uint32_t*)d_offsets, (const uint32_t*)d_sorted,
+            acc_bases, d_phi, pl.glv ? (uint32_t)n : 0x80000000u,
+            (const uint32_t*)d_offsets, acc_entries,
             (const uint32_t*)d_toff, n_keys, (const RunPlan*)d_plan, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));
     }

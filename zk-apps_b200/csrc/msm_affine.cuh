@@ -1,0 +1,250 @@
+// K4/K5 -- batched-affine pairwise summation ("affine levels") for MSMs over full digit tables.
+//
+// With the digit tables resident (msm.cu, precompute level 2) an MSM is a plain sum of affine table rows, one per
+// non-zero signed digit.  The XYZZ running sum of msm_accumulate pays 8M + 2S per row.  Here the rows are summed
+// PAIRWISE, level by level -- level 0 adds rows (2j, 2j+1) of the entry list, level 1 adds the results pairwise, ... --
+// so every addition of a level is independent of every other and all of them can share field inversions
+// (Montgomery's trick): affine + affine = 5M + 1S.
+//
+//   forward   d_i = x_Q - x_P of the lane's i-th pair;  pre[i] = d_0 d_1 ... d_i              (1 M per pair)
+//   warp      prefix / suffix product scans over the 32 lane totals with shuffles (12 M per lane), ONE inversion of
+//             the warp total -- every lane runs it on identical data, so the branchy binary Euclid of fp_inv does not
+//             diverge -- and each lane leaves with 1 / (its own total)
+//   backward  1/d_i = inv * pre[i-1];  inv *= d_i;  lambda = (y_Q - y_P) / d_i;
+//             x3 = lambda^2 - x_P - x_Q;  y3 = lambda (x_P - x3) - y_P                        (4 M + 1 S per pair)
+//
+// The inversion (shifts and subtractions, ALU pipe only) and the scans are amortised over 32 * B additions and leave
+// the multiplier -- the pipe that bounds everything else on this path -- to the other warps.
+// K levels take 1 - 2^-K of the additions; what is left (total / 2^K points) goes through msm_accumulate unchanged.
+// Proofs never mix: the entry list of every proof is padded to a multiple of 2^K with "infinity" entries
+// (table_pad_offsets / table_entries in msm.cu), so pairs never straddle a proof boundary at any level.
+//
+// Special cases are resolved per pair without breaking the product chain (they contribute the factor 1, or 2y for a
+// doubling): inf + Q, P + inf, P + (-P) = inf, P + P.  They are rare (padding, repeated bases) and sit on a divergent
+// slow path.  Replaces nothing in /root/reference (VariableBaseMSM is absent there);
+// the result is a group element, so the affine bytes are those of any other correct schedule.
+#pragma once
+#include "ec.cuh"
+
+namespace b200zk {
+
+constexpr uint32_t AFF_PAD_ENTRY = 0xffffffffu;  // entry-list padding: the point at infinity (index field all ones)
+
+#if defined(__CUDACC__)
+
+__device__ __noinline__ inline Fq fq_inv_call(Fq a) { return fp_inv_safegcd(a); }
+template <class F> DEV F aff_inv(const F& a);
+template <> DEV Fq aff_inv<Fq>(const Fq& a) { return fq_inv_call(a); }
+template <> DEV Fq2 aff_inv<Fq2>(const Fq2& a) {
+    const Fq d = fq_inv_call(fp_add(CallOps::sqr(a.c0), CallOps::sqr(a.c1)));
+    return Fq2{CallOps::mul(a.c0, d), fp_neg(CallOps::mul(a.c1, d))};
+}
+
+template <class F>
+DEV F aff_shfl(const F& a, int src_lane) {
+    F r;
+    constexpr int W = sizeof(F) / 4;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < W; i++) d[i] = __shfl_sync(0xffffffffu, s[i], src_lane);
+    return r;
+}
+
+// every lane enters with t != 0 and leaves with 1 / t: two scans, one inversion per warp
+template <class F>
+DEV F aff_warp_invert(const F& t, uint32_t lane) {
+    F pre = t, suf = t;
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        const F y = aff_shfl(pre, ((int)lane - o) & 31);  // out-of-range lanes read some lane, result unused
+        const F z = aff_shfl(suf, ((int)lane + o) & 31);
+        const F py = CallOps::mul(pre, y), sz = CallOps::mul(suf, z);
+        if ((int)lane >= o) pre = py;
+        if ((int)lane + o < 32) suf = sz;
+    }
+    const F total_inv = aff_inv(aff_shfl(pre, 31));
+    F left = aff_shfl(pre, ((int)lane - 1) & 31), right = aff_shfl(suf, ((int)lane + 1) & 31);
+    if (lane == 0) left = F::one();
+    if (lane == 31) right = F::one();
+    return CallOps::mul(CallOps::mul(total_inv, left), right);
+}
+
+enum : uint32_t { AFF_ADD = 0, AFF_DBL = 1, AFF_COPY_P = 2, AFF_COPY_Q = 3, AFF_INF = 4 };
+
+// full classification of a pair whose fast test failed (x_P = 0, x_Q = 0 or x_P = x_Q); d = the pair's factor
+template <class F>
+__device__ __noinline__ uint32_t aff_classify_slow(const Affine<F>& p, const Affine<F>& q, F& d) {
+    d = F::one();
+    if (p.is_inf()) return q.is_inf() ? AFF_INF : AFF_COPY_Q;
+    if (q.is_inf()) return AFF_COPY_P;
+    if (p.x == q.x) {
+        if (p.y == q.y && !p.y.is_zero()) {
+            d = fp_dbl(p.y);
+            return AFF_DBL;
+        }
+        return AFF_INF;  // opposite points
+    }
+    d = fp_sub(q.x, p.x);
+    return AFF_ADD;
+}
+
+// One level: out[j] = in[2j] + in[2j+1] for j < n_pairs = (*total >> shift) / 2.  FIRST: in[k] = +-table[entries[k]]
+// (bit 31 = negate, AFF_PAD_ENTRY = infinity).  A warp owns 32 * B consecutive pairs, lane l the pairs
+// warp_base + 32 i + l: consecutive lanes touch consecutive points, so the loads / stores of the upper levels and of
+// the entry list are contiguous per warp.
+template <class F, int B, bool FIRST, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine<F>* __restrict__ in,
+                                                                    const uint32_t* __restrict__ entries,
+                                                                    const uint32_t* __restrict__ total, uint32_t shift,
+                                                                    Affine<F>* __restrict__ out) {
+    constexpr int Q = sizeof(Affine<F>) / 16;  // 16-byte quads per point
+    constexpr int QX = Q / 2;                  // ... per coordinate
+    // staging, [quad][thread] so that a warp's LDS.128 / LDGSTS.128 are conflict-free.  Forward pass: two slots of
+    // (x_P, x_Q); backward pass: one slot of (P, Q).
+    __shared__ uint4 stage[2 * Q * 128];
+    uint4* my = stage + threadIdx.x;
+
+    const uint32_t n_pairs = (total[0] >> shift) >> 1;
+    const uint32_t warp_base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * (32u * B);
+    if (warp_base >= n_pairs) return;  // whole warp
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t j0 = warp_base + lane;
+    const int m = j0 < n_pairs ? (int)min((uint32_t)B, (n_pairs - j0 + 31) / 32) : 0;
+
+    auto load_entries = [&](int i) -> uint2 {
+        if constexpr (FIRST) return __ldg(reinterpret_cast<const uint2*>(entries) + (j0 + 32u * (uint32_t)i));
+        else return make_uint2(0, 0);
+    };
+    auto point_ptr = [&](int i, int which, uint32_t e) -> const Affine<F>* {
+        if constexpr (FIRST) return in + (e & 0x7fffffffu);
+        else return in + 2 * (size_t)(j0 + 32u * (uint32_t)i) + which;
+    };
+    // cp.async nq quads of the point (from quad q0) into staging quads dst0...; a padding entry stages zeros
+    auto stage_point = [&](const Affine<F>* p, bool pad, int q0, int nq, int dst0) {
+        const uint4* src = reinterpret_cast<const uint4*>(p) + q0;
+        for (int q = 0; q < nq; q++) {
+            uint4* d = my + (dst0 + q) * 128;
+            if (FIRST && pad) *d = make_uint4(0, 0, 0, 0);
+            else {
+                const uint32_t da = (uint32_t)__cvta_generic_to_shared(d);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + q));
+            }
+        }
+    };
+    auto read_coord = [&](int quad0) {
+        F r;
+        uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < QX; q++) d[q] = my[(quad0 + q) * 128];
+        return r;
+    };
+    auto load_full = [&](int i, int which, uint32_t e) {  // slow path: straight from global memory, sign applied
+        Affine<F> r = Affine<F>::inf();
+        if (FIRST && e == AFF_PAD_ENTRY) return r;
+        const uint4* src = reinterpret_cast<const uint4*>(point_ptr(i, which, e));
+        uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < Q; q++) d[q] = __ldg(src + q);
+        if (FIRST && (e >> 31)) r.y = fp_neg(r.y);
+        return r;
+    };
+
+    // ---------------------------------------------------------------- forward: running product of the denominators
+    F pre[B];
+    F acc = F::one();
+    {
+        uint2 e0 = make_uint2(0, 0), e1 = e0, e2 = e0;
+        if (0 < m) e0 = load_entries(0);
+        if (1 < m) e1 = load_entries(1);
+        if (2 < m) e2 = load_entries(2);
+        auto issue_x = [&](int slot, int i, uint2 e) {
+            if (i < m) {
+                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, 0, QX, slot * 2 * QX);
+                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, 0, QX, slot * 2 * QX + QX);
+            }
+            asm volatile("cp.async.commit_group;");  // one group per call (possibly empty): uniform accounting
+        };
+        issue_x(0, 0, e0);
+        issue_x(1, 1, e1);
+#pragma unroll 1
+        for (int i = 0; i < m; i++) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            const int slot = i & 1;
+            const F xp = read_coord(slot * 2 * QX), xq = read_coord(slot * 2 * QX + QX);
+            const uint2 ecur = e0;
+            e0 = e1;
+            e1 = e2;
+            issue_x(slot, i + 2, e1);
+            if (i + 3 < m) e2 = load_entries(i + 3);
+            F d = fp_sub(xq, xp);
+            if (xp.is_zero() || xq.is_zero() || d.is_zero()) {
+                const Affine<F> p = load_full(i, 0, ecur.x), q = load_full(i, 1, ecur.y);
+                aff_classify_slow(p, q, d);
+            }
+            acc = CallOps::mul(acc, d);
+            pre[i] = acc;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    // ---------------------------------------------------------------- one inversion per warp
+    F inv = aff_warp_invert(acc, lane);
+    // ---------------------------------------------------------------- backward: the additions
+    {
+        uint2 e_cur = make_uint2(0, 0), e_nxt = e_cur;
+        auto issue_full = [&](int i, uint2 e) {
+            if (i >= 0) {
+                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, 0, Q, 0);
+                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, 0, Q, Q);
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+        if (m > 0) e_cur = load_entries(m - 1);
+        if (m > 1) e_nxt = load_entries(m - 2);
+        issue_full(m - 1, e_cur);
+#pragma unroll 1
+        for (int i = m - 1; i >= 0; i--) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            Affine<F> p, q;
+            p.x = read_coord(0);
+            p.y = read_coord(QX);
+            q.x = read_coord(Q);
+            q.y = read_coord(Q + QX);
+            if constexpr (FIRST) {  // padding stays (0, 0): -0 = 0
+                if (e_cur.x >> 31) p.y = fp_neg(p.y);
+                if (e_cur.y >> 31) q.y = fp_neg(q.y);
+            }
+            issue_full(i - 1, e_nxt);
+            e_cur = e_nxt;
+            if (i >= 2) e_nxt = load_entries(i - 2);
+            F d = fp_sub(q.x, p.x);
+            F num = fp_sub(q.y, p.y);
+            uint32_t kind = AFF_ADD;
+            if (p.x.is_zero() || q.x.is_zero() || d.is_zero()) {
+                kind = aff_classify_slow(p, q, d);
+                if (kind == AFF_DBL) {
+                    const F xx = CallOps::sqr(p.x);
+                    num = fp_add(fp_dbl(xx), xx);
+                }
+            }
+            const F dinv = i ? CallOps::mul(inv, pre[i - 1]) : inv;
+            inv = CallOps::mul(inv, d);
+            Affine<F> r;
+            if (kind <= AFF_DBL) {
+                const F lam = CallOps::mul(num, dinv);
+                r.x = fp_sub(fp_sub(CallOps::sqr(lam), p.x), q.x);
+                r.y = fp_sub(CallOps::mul(lam, fp_sub(p.x, r.x)), p.y);
+            } else {
+                r = kind == AFF_COPY_P ? p : (kind == AFF_COPY_Q ? q : Affine<F>::inf());
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + (j0 + 32u * (uint32_t)i));
+            const uint4* src = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+            for (int qq = 0; qq < Q; qq++) dst[qq] = src[qq];
+        }
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200zk
