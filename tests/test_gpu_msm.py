@@ -209,7 +209,7 @@ def test_full_digit_table_msm(ctx, group, n, c):
     plain.free(); full.free(); win.free()
 
 
-@pytest.mark.parametrize("group,n,c,levels,b", [(1, 300, 5, 4, 32), (1, 77, 8, 3, 16), (1, 1000, 6, 1, 64), (2, 120, 4, 4, 32),
+@pytest.mark.parametrize("group,n,c,levels,b", [(1, 300, 5, 4, 32), (1, 77, 8, 3, 8), (1, 1000, 6, 1, 200), (2, 120, 4, 4, 32),
                                                 (2, 90, 5, 2, 16)])
 def test_digit_table_affine_levels(ctx, group, n, c, levels, b):
     """Full digit tables with the batched-affine pairwise levels in front of the running sums (csrc/msm_affine.cuh):
@@ -256,4 +256,4 @@ def test_digit_table_affine_levels(ctx, group, n, c, levels, b):
             h.free()
     finally:
         ctx.set_option(opt, 12)
-        ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 32)
+        ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 96)

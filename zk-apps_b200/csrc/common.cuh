@@ -53,7 +53,7 @@ struct b200zk_ctx {
     // full digit tables: rounds of pairwise batched-affine additions (csrc/msm_affine.cuh) before the XYZZ running sums
     int msm_affine_levels = 4;                             // b200zk_set_option("msm_affine_levels"): 0 = off
     long long msm_affine_min_entries = 1ll << 22;          // ... only for batches with at least this many table entries
-    int msm_affine_b = 32;                                 // additions per lane sharing one inversion per warp (16 / 32 / 64)
+    int msm_affine_b = 96;                                 // target additions per lane sharing one inversion per warp (the device plan rounds it to whole waves)
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only
     std::map<std::string, b200zk::DeviceBuf> tables;       // twiddle / coset tables; the key spells out kind, size and

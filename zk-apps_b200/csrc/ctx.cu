@@ -23,7 +23,7 @@ int b200zk_init(int device, b200zk_ctx** out) {
     if (const char* e = getenv("B200ZK_AFFINE_MIN_ENTRIES")) ctx->msm_affine_min_entries = std::max(0ll, atoll(e));
     if (const char* e = getenv("B200ZK_AFFINE_B")) {
         const int v = atoi(e);
-        if (v == 16 || v == 32 || v == 64) ctx->msm_affine_b = v;
+        if (v >= 1 && v <= 1024) ctx->msm_affine_b = v;
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -104,7 +104,7 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
         return B200ZK_OK;
     }
     if (strcmp(name, "msm_affine_b") == 0) {  // additions per lane that share one inversion per warp
-        if (value != 16 && value != 32 && value != 64) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_b must be 16, 32 or 64");
+        if (value < 1 || value > 1024) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_b must be 1..1024");
         ctx->msm_affine_b = value;
         return B200ZK_OK;
     }

@@ -756,8 +756,13 @@ __global__ void table_proof_offsets(const uint32_t* __restrict__ off, size_t n, 
 // Affine levels (msm_affine.cuh): every proof's entry list is padded to a multiple of 2^levels entries.
 // pstart[b] = padded first entry of proof b (pstart[batch] = padded total), poff_out[b] = pstart[b] >> levels = first
 // point of proof b after the last level.  One CTA, running carry over chunks of SCAN_THREADS proofs.
-__global__ void table_pad_offsets(const uint32_t* __restrict__ off, size_t n, size_t batch, uint32_t levels,
-                                  uint32_t* __restrict__ pstart, uint32_t* __restrict__ poff_out) {
+// Also the plan of the levels: B[lv] = additions per lane of level lv (pstart[batch + 1 + lv]), chosen from the real
+// entry count so that the CTAs of a level fill a whole number of waves (every lane does the same work, so a partly
+// filled last wave is pure loss): the nearest whole number of waves at the host's target B0, then
+// B = ceil(pairs / (lanes per wave * waves)), at least b_min (below that the shared inversion is no longer amortised).
+__global__ void table_pad_offsets(const uint32_t* __restrict__ off, size_t n, size_t batch, uint32_t levels, uint32_t B0,
+                                  uint32_t b_min, uint32_t lanes_per_wave, uint32_t* __restrict__ pstart,
+                                  uint32_t* __restrict__ poff_out) {
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -779,6 +784,17 @@ __global__ void table_pad_offsets(const uint32_t* __restrict__ off, size_t n, si
     if (threadIdx.x == 0) {
         pstart[batch] = carry_s;
         poff_out[batch] = carry_s >> levels;
+        for (uint32_t lv = 0; lv < levels; lv++) {
+            const uint64_t pairs = carry_s >> (lv + 1), per_wave = (uint64_t)lanes_per_wave * B0;
+            uint32_t B = B0;
+            if (lanes_per_wave) {
+                uint64_t waves = (pairs + per_wave / 2) / per_wave;
+                if (waves == 0) waves = 1;
+                const uint64_t lanes = lanes_per_wave * waves;
+                B = (uint32_t)((pairs + lanes - 1) / lanes);
+            }
+            pstart[batch + 1 + lv] = B < b_min ? b_min : B;
+        }
     }
 }
 
@@ -916,13 +932,16 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             ProfScope ps(ctx, "msm_sort", st);
             B200ZK_TRY(scratch(ctx, "msm_tab_cnt", (total + 1) * 4, &d_cnt, slot));
             B200ZK_TRY(scratch(ctx, "msm_tab_off", (total + 1) * 4, &d_off, slot));
-            if (aff_levels) B200ZK_TRY(scratch(ctx, "msm_tab_pstart", (batch + 1) * 4, &d_pstart, slot));
+            if (aff_levels) B200ZK_TRY(scratch(ctx, "msm_tab_pstart", (batch + 1 + 8) * 4, &d_pstart, slot));
             table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, h->d_skip,
                                                             (uint32_t*)d_cnt);
             B200ZK_TRY(check_launch(ctx, "table_count"));
             B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
             if (aff_levels) {
-                table_pad_offsets<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)d_off, n, batch, aff_levels, (uint32_t*)d_pstart,
+                static const int bal_env = getenv("B200ZK_AFFINE_BALANCE") ? atoi(getenv("B200ZK_AFFINE_BALANCE")) : 1;
+                const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3u : 2u) * 128u;
+                table_pad_offsets<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)d_off, n, batch, aff_levels, (uint32_t)ctx->msm_affine_b,
+                                                              AFF_B_MIN, bal_env ? aff_lanes : 0u, (uint32_t*)d_pstart,
                                                               (uint32_t*)d_offsets);
                 B200ZK_TRY(check_launch(ctx, "table_pad_offsets"));
             } else {
@@ -943,17 +962,25 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_b_g1" : "msm_aff_b_g2",
                                (size_t)(padded_entries / 4 + 1) * sizeof(Affine<F>), &d_b, slot));
             const uint32_t* d_total = (const uint32_t*)d_pstart + batch;
-            const int B = ctx->msm_affine_b;
+            // prefix products of the forward pass, [warp][i][lane]: one field element per pair of the largest level
+            // (+ one warp's worth of slack: the last warp's block is addressed whole)
+            void* d_pre;
+            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_pre_g1" : "msm_aff_pre_g2",
+                               ((size_t)(padded_entries / 2) + 32 * (size_t)AFF_B_MAX) * sizeof(F), &d_pre, slot));
             const Affine<F>* src = (const Affine<F>*)h->d_table;
             for (uint32_t lv = 0; lv < aff_levels; lv++) {
                 Affine<F>* dst = (Affine<F>*)((lv & 1) ? d_b : d_a);
                 const uint64_t max_pairs = padded_entries >> (lv + 1);
-                const unsigned grid = div_up(div_up(max_pairs, 32 * (size_t)B), 4);
+                // the grid covers the worst case of the plan (B >= 2/3 B0 with several waves, one wave otherwise); warps
+                // beyond the real count exit at once
+                const size_t B0 = std::max<size_t>(AFF_B_MIN, (size_t)ctx->msm_affine_b);
+                const size_t wave_warps = (size_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3 : 2) * 4;
+                const unsigned grid = div_up(std::max(wave_warps, (size_t)div_up(max_pairs * 3, 64 * B0)) + 1, 4);
                 constexpr int OCC = sizeof(F) == sizeof(Fq) ? 3 : 2;
-                auto kern = lv == 0 ? msm_affine_level<F, 32, true, OCC> : msm_affine_level<F, 32, false, OCC>;
-                if (B == 16) kern = lv == 0 ? msm_affine_level<F, 16, true, OCC> : msm_affine_level<F, 16, false, OCC>;
-                else if (B == 64) kern = lv == 0 ? msm_affine_level<F, 64, true, OCC> : msm_affine_level<F, 64, false, OCC>;
-                kern<<<grid, 128, 0, st>>>(src, lv == 0 ? (const uint32_t*)d_sorted : nullptr, d_total, lv, dst);
+                auto kern = lv == 0 ? msm_affine_level<F, true, OCC> : msm_affine_level<F, false, OCC>;
+                const size_t smem = aff_smem_bytes<F>(lv == 0);
+                if (smem > 48 * 1024) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<grid, 128, smem, st>>>(src, lv == 0 ? (const uint32_t*)d_sorted : nullptr, d_total, lv, dst, (F*)d_pre);
                 B200ZK_TRY(check_launch(ctx, "msm_affine_level"));
                 src = dst;
             }

@@ -29,6 +29,7 @@
 namespace b200zk {
 
 constexpr uint32_t AFF_PAD_ENTRY = 0xffffffffu;  // entry-list padding: the point at infinity (index field all ones)
+constexpr uint32_t AFF_B_MIN = 8, AFF_B_MAX = 1024;  // additions per lane that share one inversion per warp
 
 #if defined(__CUDACC__)
 
@@ -89,47 +90,73 @@ __device__ __noinline__ uint32_t aff_classify_slow(const Affine<F>& p, const Aff
     return AFF_ADD;
 }
 
-// One level: out[j] = in[2j] + in[2j+1] for j < n_pairs = (*total >> shift) / 2.  FIRST: in[k] = +-table[entries[k]]
+// Shared memory of one CTA of msm_affine_level, in bytes (dynamic: the G2 build needs more than 48 KB)
+template <class F>
+constexpr size_t aff_smem_bytes(bool first) {
+    constexpr size_t Q = sizeof(Affine<F>) / 16;
+    return (2 * Q + Q / 2) * 16 * 128 + (first ? 8 * 8 * 128 : 0);
+}
+
+// One level: out[j] = in[2j] + in[2j+1] for j < n_pairs = (total[0] >> shift) / 2; total[1 + shift] = B of the level.  FIRST: in[k] = +-table[entries[k]]
 // (bit 31 = negate, AFF_PAD_ENTRY = infinity).  A warp owns 32 * B consecutive pairs, lane l the pairs
 // warp_base + 32 i + l: consecutive lanes touch consecutive points, so the loads / stores of the upper levels and of
 // the entry list are contiguous per warp.
-template <class F, int B, bool FIRST, int MIN_BLOCKS>
+//
+// Everything the two loops consume arrives through cp.async (LDGSTS) into shared memory, issued iterations ahead:
+// the table rows, the entries that address them, and -- on the way back -- the prefix products the forward pass left
+// in `pre_g` ([warp][i][lane], global scratch).  A plain load would be waited for at the next CALL (the field products
+// are calls, ec.cuh), i.e. its whole latency exposed once per pair; an asynchronous copy is only waited for when its
+// data is read.  One commit group per iteration:
+//   forward   G_i = { x_P, x_Q of pair i + 2;  entries of pair i + 4 },        wait_group 1 at the top of iteration i
+//   backward  G_i = { P, Q of pair i - 1;  pre[i - 2];  entries of pair i - 3 }, wait_group 0
+template <class F, bool FIRST, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine<F>* __restrict__ in,
                                                                     const uint32_t* __restrict__ entries,
                                                                     const uint32_t* __restrict__ total, uint32_t shift,
-                                                                    Affine<F>* __restrict__ out) {
+                                                                    Affine<F>* __restrict__ out, F* __restrict__ pre_g) {
     constexpr int Q = sizeof(Affine<F>) / 16;  // 16-byte quads per point
     constexpr int QX = Q / 2;                  // ... per coordinate
     // staging, [quad][thread] so that a warp's LDS.128 / LDGSTS.128 are conflict-free.  Forward pass: two slots of
-    // (x_P, x_Q); backward pass: one slot of (P, Q).
-    __shared__ uint4 stage[2 * Q * 128];
-    uint4* my = stage + threadIdx.x;
+    // (x_P, x_Q) = 4 QX quads; backward pass: one slot of (P, Q, pre) = 2 Q + QX quads.  Then the entry ring.
+    extern __shared__ uint4 aff_smem[];
+    uint4* my = aff_smem + threadIdx.x;
+    uint2* ering = reinterpret_cast<uint2*>(aff_smem + (2 * Q + QX) * 128) + threadIdx.x;  // [slot & 7][thread]
 
     const uint32_t n_pairs = (total[0] >> shift) >> 1;
-    const uint32_t warp_base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * (32u * B);
+    const uint32_t B = min(total[1 + shift], AFF_B_MAX);  // plan of this level (table_pad_offsets)
+    const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t warp_base = warp * (32u * B);
     if (warp_base >= n_pairs) return;  // whole warp
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t j0 = warp_base + lane;
-    const int m = j0 < n_pairs ? (int)min((uint32_t)B, (n_pairs - j0 + 31) / 32) : 0;
+    const int m = j0 < n_pairs ? (int)min(B, (n_pairs - j0 + 31) / 32) : 0;
+    F* my_pre = pre_g + (size_t)warp * (32u * B) + lane;  // pre[i] at my_pre[32 i]
 
-    auto load_entries = [&](int i) -> uint2 {
-        if constexpr (FIRST) return __ldg(reinterpret_cast<const uint2*>(entries) + (j0 + 32u * (uint32_t)i));
+    auto cp16 = [](uint4* dst, const uint4* src) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+    };
+    auto e_fetch = [&](int i) {
+        if constexpr (FIRST) {
+            if (i >= 0 && i < m)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(ering + (i & 7) * 128)),
+                             "l"(reinterpret_cast<const uint2*>(entries) + (j0 + 32u * (uint32_t)i)));
+        }
+    };
+    auto e_get = [&](int i) -> uint2 {
+        if constexpr (FIRST) return ering[(i & 7) * 128];
         else return make_uint2(0, 0);
     };
     auto point_ptr = [&](int i, int which, uint32_t e) -> const Affine<F>* {
         if constexpr (FIRST) return in + (e & 0x7fffffffu);
         else return in + 2 * (size_t)(j0 + 32u * (uint32_t)i) + which;
     };
-    // cp.async nq quads of the point (from quad q0) into staging quads dst0...; a padding entry stages zeros
-    auto stage_point = [&](const Affine<F>* p, bool pad, int q0, int nq, int dst0) {
-        const uint4* src = reinterpret_cast<const uint4*>(p) + q0;
+    // cp.async nq quads of the point into staging quads dst0...; a padding entry stages zeros
+    auto stage_point = [&](const Affine<F>* p, bool pad, int nq, int dst0) {
+        const uint4* src = reinterpret_cast<const uint4*>(p);
         for (int q = 0; q < nq; q++) {
             uint4* d = my + (dst0 + q) * 128;
             if (FIRST && pad) *d = make_uint4(0, 0, 0, 0);
-            else {
-                const uint32_t da = (uint32_t)__cvta_generic_to_shared(d);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + q));
-            }
+            else cp16(d, src + q);
         }
     };
     auto read_coord = [&](int quad0) {
@@ -149,41 +176,45 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
         if (FIRST && (e >> 31)) r.y = fp_neg(r.y);
         return r;
     };
+    auto commit = [] { asm volatile("cp.async.commit_group;"); };
 
     // ---------------------------------------------------------------- forward: running product of the denominators
-    F pre[B];
     F acc = F::one();
     {
-        uint2 e0 = make_uint2(0, 0), e1 = e0, e2 = e0;
-        if (0 < m) e0 = load_entries(0);
-        if (1 < m) e1 = load_entries(1);
-        if (2 < m) e2 = load_entries(2);
-        auto issue_x = [&](int slot, int i, uint2 e) {
+        auto issue_x = [&](int i) {  // x_P, x_Q of pair i -> slot i & 1 (entries of pair i already in the ring)
             if (i < m) {
-                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, 0, QX, slot * 2 * QX);
-                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, 0, QX, slot * 2 * QX + QX);
+                const uint2 e = e_get(i);
+                const int slot = (i & 1) * 2 * QX;
+                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, QX, slot);
+                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, QX, slot + QX);
             }
-            asm volatile("cp.async.commit_group;");  // one group per call (possibly empty): uniform accounting
         };
-        issue_x(0, 0, e0);
-        issue_x(1, 1, e1);
+        e_fetch(0); e_fetch(1); e_fetch(2); e_fetch(3);
+        commit();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        issue_x(0);
+        commit();
+        issue_x(1);
+        commit();
 #pragma unroll 1
         for (int i = 0; i < m; i++) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");
-            const int slot = i & 1;
-            const F xp = read_coord(slot * 2 * QX), xq = read_coord(slot * 2 * QX + QX);
-            const uint2 ecur = e0;
-            e0 = e1;
-            e1 = e2;
-            issue_x(slot, i + 2, e1);
-            if (i + 3 < m) e2 = load_entries(i + 3);
+            const int slot = (i & 1) * 2 * QX;
+            const F xp = read_coord(slot), xq = read_coord(slot + QX);
+            const uint2 ecur = e_get(i);
+            issue_x(i + 2);
+            e_fetch(i + 4);
+            commit();
             F d = fp_sub(xq, xp);
             if (xp.is_zero() || xq.is_zero() || d.is_zero()) {
                 const Affine<F> p = load_full(i, 0, ecur.x), q = load_full(i, 1, ecur.y);
                 aff_classify_slow(p, q, d);
             }
             acc = CallOps::mul(acc, d);
-            pre[i] = acc;
+            uint4* dst = reinterpret_cast<uint4*>(my_pre + 32 * i);
+            const uint4* src = reinterpret_cast<const uint4*>(&acc);
+#pragma unroll
+            for (int qq = 0; qq < QX; qq++) dst[qq] = src[qq];
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -191,17 +222,24 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
     F inv = aff_warp_invert(acc, lane);
     // ---------------------------------------------------------------- backward: the additions
     {
-        uint2 e_cur = make_uint2(0, 0), e_nxt = e_cur;
-        auto issue_full = [&](int i, uint2 e) {
+        auto issue_full = [&](int i) {  // P, Q of pair i and pre[i - 1] -> the slot
             if (i >= 0) {
-                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, 0, Q, 0);
-                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, 0, Q, Q);
+                const uint2 e = e_get(i);
+                stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, Q, 0);
+                stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, Q, Q);
+                if (i > 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(my_pre + 32 * (i - 1));
+#pragma unroll
+                    for (int qq = 0; qq < QX; qq++) cp16(my + (2 * Q + qq) * 128, src + qq);
+                }
             }
-            asm volatile("cp.async.commit_group;");
         };
-        if (m > 0) e_cur = load_entries(m - 1);
-        if (m > 1) e_nxt = load_entries(m - 2);
-        issue_full(m - 1, e_cur);
+        e_fetch(m - 1); e_fetch(m - 2);
+        commit();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        issue_full(m - 1);
+        e_fetch(m - 3);
+        commit();
 #pragma unroll 1
         for (int i = m - 1; i >= 0; i--) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -210,13 +248,15 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
             p.y = read_coord(QX);
             q.x = read_coord(Q);
             q.y = read_coord(Q + QX);
+            const F pre_prev = read_coord(2 * Q);  // garbage for i = 0, unused
+            const uint2 ecur = e_get(i);
             if constexpr (FIRST) {  // padding stays (0, 0): -0 = 0
-                if (e_cur.x >> 31) p.y = fp_neg(p.y);
-                if (e_cur.y >> 31) q.y = fp_neg(q.y);
+                if (ecur.x >> 31) p.y = fp_neg(p.y);
+                if (ecur.y >> 31) q.y = fp_neg(q.y);
             }
-            issue_full(i - 1, e_nxt);
-            e_cur = e_nxt;
-            if (i >= 2) e_nxt = load_entries(i - 2);
+            issue_full(i - 1);
+            e_fetch(i - 3);
+            commit();
             F d = fp_sub(q.x, p.x);
             F num = fp_sub(q.y, p.y);
             uint32_t kind = AFF_ADD;
@@ -227,7 +267,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
                     num = fp_add(fp_dbl(xx), xx);
                 }
             }
-            const F dinv = i ? CallOps::mul(inv, pre[i - 1]) : inv;
+            const F dinv = i ? CallOps::mul(inv, pre_prev) : inv;
             inv = CallOps::mul(inv, d);
             Affine<F> r;
             if (kind <= AFF_DBL) {
