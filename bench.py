@@ -33,6 +33,8 @@ UNIT = "proofs/s"
 TREE_HEIGHT = 10
 TOXIC = (0x1f2e3d4c5b6a7988, 0x0123456789abcdef, 0x0fedcba987654321, 0x1122334455667788, 0x99aabbccddeeff00)
 FQ_MUL_PER_MADD = 10          # XYZZ mixed addition 8M + 2S
+FQ_MUL_PER_AFFINE_ADD = 6     # batched-affine addition 5M + 1S (csrc/msm_affine.cuh), the shared inversion not counted
+AFFINE_BYTES_PER_ADD = 292    # algorithmic: two 96-byte points in (+ two 4-byte entries at level 0), one 96-byte point out
 IMAD_WIDE_PER_FQ_MUL = 300    # 2*12^2 + 12
 
 
@@ -270,7 +272,7 @@ def kernel_source_hash() -> str:
     when it was taken on exactly this code."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("msm.cu", "ec.cuh", "field.cuh", "field_asm.cuh", "glv.cuh"):
+    for f in ("msm.cu", "msm_affine.cuh", "ec.cuh", "field.cuh", "field_asm.cuh", "glv.cuh"):
         h.update(open(os.path.join(ROOT, "zk-apps_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
@@ -549,7 +551,8 @@ def run_b200(args):
     ms_serial = time_ms_events(ctx, step_resident, prof_steps)
     prof = {k: ctx.prof_get(k) for k in ctx.prof_names()}
     entries_g1, entries_g2 = ctx.stat_get("msm_entries_g1"), ctx.stat_get("msm_entries_g2")
-    buckets_g1 = ctx.stat_get("msm_buckets_g1")
+    aff_adds_g1, aff_adds_g2 = ctx.stat_get("msm_affine_adds_g1"), ctx.stat_get("msm_affine_adds_g2")
+    ctx_affine_levels = int(os.environ.get("B200ZK_AFFINE_LEVELS", "4"))
     ctx.prof_enable(False)
     ctx.set_option("concurrency", 1)
     if args.timeline and rank == 0:
@@ -587,54 +590,81 @@ def run_b200(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel: msm_accumulate<Fq> (G1 bucket accumulation)
+    # ---- roofline of the dominant kernel: msm_affine_level<Fq> (G1, batched-affine pairwise additions over the digit
+    #      tables); with affine levels off (msm_affine_levels = 0 / --precompute < 2) it is msm_accumulate<Fq>
     acc_ms, acc_launches = prof.get("msm_accumulate_g1", (0.0, 0))
     acc2_ms, acc2_launches = prof.get("msm_accumulate_g2", (0.0, 0))
+    aff_ms, aff_brackets = prof.get("msm_affine_g1", (0.0, 0))          # one bracket = the levels of one MSM
+    aff2_ms, aff2_brackets = prof.get("msm_affine_g2", (0.0, 0))
     peaks_path = os.path.join(ROOT, "profiles", "r02_int_peaks.json")
     if not os.path.exists(peaks_path):
         peaks_path = os.path.join(ROOT, "profiles", "r01_int_peaks.json")
     int_peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     fq_peak = int_peaks.get("fq_mul_per_s")
-    per_launch_ms = acc_ms / max(1, acc_launches)
-    madds_per_launch = entries_g1 / max(1, acc_launches)
-    alg_bytes = madds_per_launch * (96 + 4) + buckets_g1 / max(1, acc_launches) * 192
+    affine = aff_adds_g1 > 0 and aff_ms > 0
+    levels = ctx_affine_levels if affine else 0
+    if affine:
+        kern_name = "msm_affine_level<Fq> (G1, batched-affine pairwise additions over the digit tables, 5M + 1S each)"
+        dom_ms, dom_launches = aff_ms, aff_brackets * levels
+        units_per_launch = aff_adds_g1 / max(1, dom_launches)
+        mul_per_unit, bytes_per_unit = FQ_MUL_PER_AFFINE_ADD, AFFINE_BYTES_PER_ADD
+    else:
+        kern_name = "msm_accumulate<Fq> (G1 bucket accumulation, XYZZ += affine)"
+        dom_ms, dom_launches = acc_ms, acc_launches
+        units_per_launch = entries_g1 / max(1, dom_launches)
+        mul_per_unit, bytes_per_unit = FQ_MUL_PER_MADD, 96 + 4
+    per_launch_ms = dom_ms / max(1, dom_launches)
+    alg_bytes = units_per_launch * bytes_per_unit
     achieved_gbs = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
-    fq_mul_s = madds_per_launch * FQ_MUL_PER_MADD / (per_launch_ms * 1e-3) if per_launch_ms else 0.0
+    fq_mul_s = units_per_launch * mul_per_unit / (per_launch_ms * 1e-3) if per_launch_ms else 0.0
     # DRAM bytes per launch from an `ncu --set full` capture: attached only when the capture was taken on exactly
-    # the kernel sources this run was built from (tools/ncu_traffic.py stamps it with their hash)
+    # the kernel sources this run was built from (tools/ncu_summarise.py stamps it with their hash)
     traffic, traffic_note = None, "no ncu capture of the current kernel sources under profiles/"
-    tp = os.path.join(ROOT, "profiles", "r02_msm_accumulate_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_msm_affine_traffic.json" if affine else "r02_msm_accumulate_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if tj.get("source_hash") == kernel_source_hash():
             traffic, traffic_note = tj.get("dram_bytes_per_launch"), "ncu --set full, %s" % tj.get("capture", "profiles/")
         else:
-            traffic_note = "profiles/r02_msm_accumulate_traffic.json was captured on other kernel sources: not attached"
-    # G2: the algorithmic count of SURVEY.md section 8d (Fq2 product = 3 Fq products): 30 Fq-mul equivalents per mixed addition
-    fq2_mul_s = (entries_g2 / max(1, acc2_launches)) * 3 * FQ_MUL_PER_MADD / (acc2_ms / max(1, acc2_launches) * 1e-3) if acc2_ms else 0.0
-    step_fq_mul = (entries_g1 + 3 * entries_g2) * FQ_MUL_PER_MADD / prof_steps          # per step, bucket accumulation only
+            traffic_note = "%s was captured on other kernel sources: not attached" % os.path.relpath(tp, ROOT)
+    # the XYZZ running sums over what the affine levels leave (1 / 2^levels of the entries), or over everything
+    xyzz_mul_s = entries_g1 * FQ_MUL_PER_MADD / (acc_ms * 1e-3) if acc_ms else 0.0
+    # G2: the algorithmic count of SURVEY.md section 8d (Fq2 product = 3 Fq products)
+    g2_mul_equiv = aff_adds_g2 * 3 * FQ_MUL_PER_AFFINE_ADD + entries_g2 * 3 * FQ_MUL_PER_MADD
+    g2_ms = aff2_ms + acc2_ms
+    fq2_mul_s = g2_mul_equiv / (g2_ms * 1e-3) if g2_ms else 0.0
+    step_fq_mul = ((aff_adds_g1 + 3 * aff_adds_g2) * FQ_MUL_PER_AFFINE_ADD + (entries_g1 + 3 * entries_g2) * FQ_MUL_PER_MADD) / prof_steps
     step_frac = step_fq_mul / ((ms / args.steps) * 1e-3) / fq_peak if fq_peak else None
     int_g1_frac = (fq_mul_s / fq_peak) if fq_peak else None
-    roofline = {"kernel": "msm_accumulate<Fq> (G1 bucket accumulation, XYZZ += affine)", "bound": "hbm",
+    roofline = {"kernel": kern_name, "bound": "hbm",
                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src, "launch_ms": per_launch_ms,
-                "launches": acc_launches, "share_of_step": acc_ms / ms_serial if ms_serial else None,
+                "launches": dom_launches, "share_of_step": dom_ms / ms_serial if ms_serial else None,
+                "algorithmic_bytes_per_addition": bytes_per_unit,
                 "binding": "int", "binding_frac": int_g1_frac,
                 "note": "the kernel is bound by the integer-multiply pipe, not by HBM (SURVEY.md section 0 item 4): the HBM "
                         "fraction is reported because the contract asks for it; `binding_frac` = `int.frac` is the one that binds",
                 "int": {"bound": "imad_wide", "achieved": fq_mul_s * IMAD_WIDE_PER_FQ_MUL / 1e12,
                         "peak": (fq_peak * IMAD_WIDE_PER_FQ_MUL / 1e12) if fq_peak else None, "unit": "T IMAD.WIDE/s",
                         "frac": int_g1_frac, "achieved_fq_mul_per_s": fq_mul_s,
-                        "peak_fq_mul_per_s": fq_peak, "mixed_additions_per_launch": madds_per_launch,
+                        "peak_fq_mul_per_s": fq_peak, "additions_per_launch": units_per_launch,
+                        "fq_mul_per_addition": mul_per_unit, "affine_levels": levels,
                         "peak_source": "measured: back-to-back Fq Montgomery products on all SMs (%s)" % os.path.relpath(peaks_path, ROOT)},
-                "int_g2": {"kernel": "msm_accumulate<Fq2> (G2 bucket accumulation)", "bound": "imad_wide",
+                "int_xyzz": {"kernel": "msm_accumulate<Fq> (XYZZ running sums over the points the affine levels leave)",
+                             "frac": (xyzz_mul_s / fq_peak) if fq_peak else None, "ms": acc_ms, "launches": acc_launches,
+                             "mixed_additions": entries_g1, "fq_mul_per_addition": FQ_MUL_PER_MADD},
+                "int_g2": {"kernel": "msm_affine_level<Fq2> + msm_accumulate<Fq2> (G2)", "bound": "imad_wide",
                            "frac": (fq2_mul_s / fq_peak) if fq_peak else None, "achieved_fq_mul_equiv_per_s": fq2_mul_s,
-                           "launch_ms": acc2_ms / max(1, acc2_launches), "launches": acc2_launches,
-                           "mixed_additions_per_launch": entries_g2 / max(1, acc2_launches),
-                           "note": "30 Fq-mul equivalents per G2 mixed addition (SURVEY.md section 8d count; the kernel spends 28)"},
-                "int_step": {"frac": step_frac, "fq_mul_equiv_per_step": step_fq_mul, "msm_entries_g1": entries_g1 / prof_steps,
-                             "msm_entries_g2": entries_g2 / prof_steps,
-                             "note": "whole step: Fq-mul equivalents of the bucket accumulations (G1 + G2) / ms_per_step / measured Fq-mul peak"}}
+                           "ms": g2_ms, "affine_additions": aff_adds_g2, "mixed_additions": entries_g2,
+                           "note": "Fq-mul equivalents with an Fq2 product = 3 Fq products (SURVEY.md section 8d): 18 per affine "
+                                   "addition, 30 per XYZZ mixed addition"},
+                "int_step": {"frac": step_frac, "fq_mul_equiv_per_step": step_fq_mul,
+                             "affine_additions_g1": aff_adds_g1 / prof_steps, "affine_additions_g2": aff_adds_g2 / prof_steps,
+                             "msm_entries_g1": entries_g1 / prof_steps, "msm_entries_g2": entries_g2 / prof_steps,
+                             "note": "whole step: Fq-mul equivalents the MSM additions actually spend (G1 + G2; 6 per affine, 10 per "
+                                     "XYZZ addition) / ms_per_step / measured Fq-mul peak.  The affine levels cut the WORK per proof "
+                                     "(6 instead of 10 products per addition), so this fraction is not comparable with a line "
+                                     "measured without them; proofs/s is"}}
     kernel_ms = {k: v[0] / prof_steps for k, v in prof.items()}
     kernel_ms["_serialised_step_ms"] = ms_serial / prof_steps
     # ---- CPU baseline beside it (bounded sample)
