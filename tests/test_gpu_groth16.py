@@ -312,7 +312,7 @@ def test_proofs_over_full_digit_tables(ctx, withdraw_key):
     ctx.set_option("table_c_g1", 4); ctx.set_option("table_c_g2", 3)
     pk2 = z.Groth16.generate_parameters_with_toxic_waste(ctx, relation, (TOX.alpha, TOX.beta, TOX.gamma, TOX.delta, TOX.tau),
                                                          precompute=2)
-    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 12)
+    ctx.set_option("table_c_g1", 13); ctx.set_option("table_c_g2", 13)
     B = 6
     ws = [rel.make_witness(300 + i, rel.WITHDRAW) for i in range(B)]
     inputs = util.fr_mont_array([v for w in ws for v in rel.witness_to_inputs(w)])

@@ -195,7 +195,7 @@ def test_full_digit_table_msm(ctx, group, n, c):
     want, want_inf = plain.msm(ss.reshape(-1), n=n, batch=batch)
     ctx.set_option("table_c_g1" if group == 1 else "table_c_g2", c)
     full = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=2)
-    ctx.set_option("table_c_g1", 12); ctx.set_option("table_c_g2", 12)
+    ctx.set_option("table_c_g1", 13); ctx.set_option("table_c_g2", 13)
     got, got_inf = full.msm(ss.reshape(-1), n=n, batch=batch)
     assert bytes(got) == bytes(want) and list(got_inf) == list(want_inf) and got_inf[2] == 1
     one, _ = full.msm(ss[1].reshape(-1), n=n)                        # batch of one, host scalars
@@ -255,5 +255,5 @@ def test_digit_table_affine_levels(ctx, group, n, c, levels, b):
                 assert res == expect and bool(inf[0]) == (expect is None), (name, s)
             h.free()
     finally:
-        ctx.set_option(opt, 12)
+        ctx.set_option(opt, 13)
         ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 96)

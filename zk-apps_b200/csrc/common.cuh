@@ -48,7 +48,7 @@ struct b200zk_ctx {
     bool concurrency = true;                               // b200zk_set_option("concurrency")
     int msm_parts = 0;                                     // b200zk_set_option("msm_parts"): 0 = automatic
     bool msm_glv = true;                                   // b200zk_set_option("msm_glv"): GLV for plain G1 bases
-    int table_c_g1 = 12, table_c_g2 = 12;                  // window of a full digit table (precompute level 2): the table
+    int table_c_g1 = 13, table_c_g2 = 13;                  // window of a full digit table (precompute level 2): the table
                                                            // holds n * ceil(256 / c) * 2^(c-1) points
     // full digit tables: rounds of pairwise batched-affine additions (csrc/msm_affine.cuh) before the XYZZ running sums
     int msm_affine_levels = 4;                             // b200zk_set_option("msm_affine_levels"): 0 = off

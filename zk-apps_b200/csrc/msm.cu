@@ -41,6 +41,8 @@ struct Plan {
     uint32_t w0, w1;              // windows [w0, w1) this pass of the pipeline handles (all of them unless split)
     bool glv;                     // plain bases: every scalar is k1 + k2*lambda, entries (k1, P_i) and (k2, phi(P_i))
     bool table = false;           // precompute level 2: full digit table, "bucket" = the whole MSM of one proof
+    bool tglv = false;            // ... over GLV half scalars: the `batch` of a pass counts (proof, half) pairs, half 0 = k1
+                                  // (sum over the table rows as they are), half 1 = k2 (the same rows, phi applied to the sum)
     uint32_t mult = 0;            // table entries per (window, base) = 2^(c-1)
     size_t n_table = 0;           // bases per window in a precomputed table (= bases of the handle, >= scalars of a call)
 };
@@ -68,11 +70,12 @@ uint32_t pick_window(size_t n, bool precomp, bool glv) {
     return best_c;
 }
 
-Plan make_plan(size_t n, bool precomp, uint32_t c_fixed, bool glv = false) {
+Plan make_plan(size_t n, bool precomp, uint32_t c_fixed, bool glv = false, bool table_glv = false) {
     Plan p;
     p.glv = glv && !precomp;
+    p.tglv = table_glv;
     p.c = c_fixed ? c_fixed : pick_window(n, precomp, p.glv);
-    p.windows = ((p.glv ? GLV_BITS : 256) + p.c - 1) / p.c;
+    p.windows = (((p.glv || p.tglv) ? GLV_BITS : 256) + p.c - 1) / p.c;
     p.nb = 1u << (p.c - 1);
     p.precomp = precomp;
     p.weff = precomp ? 1 : p.windows;
@@ -645,6 +648,19 @@ __global__ void __launch_bounds__(32) msm_finish(const XYZZ<F>* __restrict__ wsu
     out[b] = ec_to_affine(acc);
 }
 
+// digit tables over GLV half scalars: sums[2 b] = sum of the k1 rows, sums[2 b + 1] = sum of the k2 rows of proof b;
+// phi is a homomorphism, so the k2 part of the MSM is phi of that sum: out[b] = sums[2 b] + phi(sums[2 b + 1])
+template <class F>
+__global__ void __launch_bounds__(32) msm_finish_glv(const XYZZ<F>* __restrict__ sums, uint32_t batch, Affine<F>* __restrict__ out) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    XYZZ<F> acc = sums[2 * (size_t)b];
+    XYZZ<F> s2 = sums[2 * (size_t)b + 1];
+    s2.x = glv_phi_x(s2.x);  // x = X / ZZ: scaling X scales x
+    ec_add<F, CallOps>(acc, s2);
+    out[b] = ec_to_affine(acc);
+}
+
 // table[w*n + i] = 2^c * table[(w-1)*n + i]
 template <class F>
 __global__ void __launch_bounds__(64) msm_precompute_step(const Affine<F>* __restrict__ prev, size_t n, uint32_t c,
@@ -703,15 +719,29 @@ __global__ void __launch_bounds__(32) points_sum_kernel(const Affine<F>* __restr
 // the runs of a proof are then added by one CTA (msm_sum_partials).
 
 // number of non-zero digits of scalar (b, i)
+// scalar (b, i) of a table pass; tglv: b counts (proof, half) pairs and k is that GLV half (upper limbs zero)
+__device__ __forceinline__ void load_table_scalar(const uint32_t* scalars, size_t b, size_t i, size_t stride, bool mont, bool tglv,
+                                                  uint32_t* k) {
+    if (!tglv) {
+        load_scalar(scalars, b * stride + i, mont, k);
+        return;
+    }
+    uint32_t full[8], k1[GLV_LIMBS], k2[GLV_LIMBS];
+    load_scalar(scalars, (b >> 1) * stride + i, mont, full);
+    glv_split(full, k1, k2);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = j < GLV_LIMBS ? ((b & 1) ? k2[j] : k1[j]) : 0u;
+}
+
 __global__ void table_count(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, uint32_t c,
-                            uint32_t windows, const uint8_t* __restrict__ skip, uint32_t* __restrict__ counts) {
+                            uint32_t windows, int tglv, const uint8_t* __restrict__ skip, uint32_t* __restrict__ counts) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= n * batch) return;
     const size_t b = t / n, i = t % n;
     uint32_t cnt = 0;
     if (!(skip && skip[i])) {
         uint32_t k[8];
-        load_scalar(scalars, b * stride + i, mont != 0, k);
+        load_table_scalar(scalars, b, i, stride, mont != 0, tglv != 0, k);
         uint32_t carry = 0;
         for (uint32_t w = 0; w < windows; w++) cnt += next_digit(k, w, c, carry) != 0 ? 1u : 0u;
     }
@@ -722,7 +752,7 @@ __global__ void table_count(const uint32_t* scalars, size_t n, size_t stride, si
 // pstart (optional): padded first entry of every proof (table_pad_offsets); the list of proof b then lives at
 // pstart[b]... and the thread of its last scalar fills the gap up to pstart[b + 1] with AFF_PAD_ENTRY
 __global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, size_t batch, int mont, uint32_t c,
-                              uint32_t windows, uint32_t mult, const uint8_t* __restrict__ skip,
+                              uint32_t windows, uint32_t mult, int tglv, const uint8_t* __restrict__ skip,
                               const uint32_t* __restrict__ off, const uint32_t* __restrict__ pstart,
                               uint32_t* __restrict__ entries) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -737,7 +767,7 @@ __global__ void table_entries(const uint32_t* scalars, size_t n, size_t stride, 
     }
     if (skip && skip[i]) return;
     uint32_t k[8];
-    load_scalar(scalars, b * stride + i, mont != 0, k);
+    load_table_scalar(scalars, b, i, stride, mont != 0, tglv != 0, k);
     uint32_t carry = 0;
     for (uint32_t w = 0; w < windows; w++) {
         const int32_t d = next_digit(k, w, c, carry);
@@ -933,8 +963,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             B200ZK_TRY(scratch(ctx, "msm_tab_cnt", (total + 1) * 4, &d_cnt, slot));
             B200ZK_TRY(scratch(ctx, "msm_tab_off", (total + 1) * 4, &d_off, slot));
             if (aff_levels) B200ZK_TRY(scratch(ctx, "msm_tab_pstart", (batch + 1 + 8) * 4, &d_pstart, slot));
-            table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, h->d_skip,
-                                                            (uint32_t*)d_cnt);
+            table_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows,
+                                                            pl.tglv ? 1 : 0, h->d_skip, (uint32_t*)d_cnt);
             B200ZK_TRY(check_launch(ctx, "table_count"));
             B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
             if (aff_levels) {
@@ -949,7 +979,7 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
                 B200ZK_TRY(check_launch(ctx, "table_proof_offsets"));
             }
             table_entries<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl.c, pl.windows, pl.mult,
-                                                              h->d_skip, (const uint32_t*)d_off, (const uint32_t*)d_pstart,
+                                                              pl.tglv ? 1 : 0, h->d_skip, (const uint32_t*)d_off, (const uint32_t*)d_pstart,
                                                               (uint32_t*)d_sorted);
             B200ZK_TRY(check_launch(ctx, "table_entries"));
         }
@@ -962,8 +992,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_b_g1" : "msm_aff_b_g2",
                                (size_t)(padded_entries / 4 + 1) * sizeof(Affine<F>), &d_b, slot));
             const uint32_t* d_total = (const uint32_t*)d_pstart + batch;
-            // prefix products of the forward pass, [warp][i][lane]: one field element per pair of the largest level
-            // (+ one warp's worth of slack: the last warp's block is addressed whole)
+            // prefix products of the forward pass, [row][quad][lane]: one field element per pair of the largest level
+            // (+ slack: the last rows are addressed whole)
             void* d_pre;
             B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_pre_g1" : "msm_aff_pre_g2",
                                ((size_t)(padded_entries / 2) + 32 * (size_t)AFF_B_MAX) * sizeof(F), &d_pre, slot));
@@ -1182,8 +1212,8 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     // plain bases: GLV halves the scalar length (glv.cuh); the phi half of the table is rebuilt per call
     // (n products, one pass over the points) so the handle stays a plain array of the caller's bases
     const bool glv = !h->precomputed && ctx->msm_glv && n >= 2;
-    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0, glv);
-    if (h->d_table) {  // full digit table: one "bucket" per MSM of the batch
+    Plan pl = make_plan(h->n, h->precomputed != 0, h->precomputed ? h->c : 0, glv, h->d_table && h->table_glv);
+    if (h->d_table) {  // full digit table: one "bucket" per MSM of the batch (two with GLV half scalars)
         pl.table = true;
         pl.mult = h->mult;
         pl.weff = 1;
@@ -1206,7 +1236,7 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     parts = std::min(parts, pl.windows);
     const XYZZ<F>* sums = nullptr;
     if (parts == 1) {
-        B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, batch, mont, pl, slot, d_phi, &sums));
+        B200ZK_TRY(msm_part<F>(ctx, h, d_scalars, n, stride, pl.tglv ? 2 * batch : batch, mont, pl, slot, d_phi, &sums));
     } else {
         static const int part_slot[4] = {0, 5, 6, 8};   // streams: main, aux[0], aux[1], aux[3] (priority order)
         void* d_ws;
@@ -1234,7 +1264,8 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     }
     {
         ProfScope ps(ctx, "msm_reduce", st);
-        msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(sums, (uint32_t)batch, pl.weff, pl.c, d_out);
+        if (pl.tglv) msm_finish_glv<F><<<div_up(batch, 32), 32, 0, st>>>(sums, (uint32_t)batch, d_out);
+        else msm_finish<F><<<div_up(batch, 32), 32, 0, st>>>(sums, (uint32_t)batch, pl.weff, pl.c, d_out);
         B200ZK_TRY(check_launch(ctx, "msm_finish"));
     }
     return B200ZK_OK;
@@ -1254,7 +1285,11 @@ int bases_build(b200zk_ctx* ctx, b200zk_bases* h, const Affine<F>* d_src, bool s
         c_table = sizeof(F) == sizeof(Fq) ? (uint32_t)ctx->table_c_g1 : (uint32_t)ctx->table_c_g2;
         if (c_table < 2 || c_table > 16) return fail(ctx, B200ZK_ERR_BAD_ARG, "table_c_g1 / table_c_g2 must be 2..16");
     }
-    Plan pl = make_plan(n, precompute != 0, c_table);
+    // full digit tables are built over GLV half scalars (130 instead of 256 bits of windows: half the table, so a
+    // wider window fits) unless msm_glv is off; like the plain GLV path this needs the bases in the order-r subgroup
+    const bool table_glv = precompute >= 2 && ctx->msm_glv;
+    Plan pl = make_plan(n, precompute != 0, c_table, false, table_glv);
+    h->table_glv = table_glv ? 1 : 0;
     h->n = n;
     h->precomputed = precompute ? 1 : 0;
     h->c = pl.c;

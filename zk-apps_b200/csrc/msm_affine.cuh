@@ -98,13 +98,12 @@ constexpr size_t aff_smem_bytes(bool first) {
 }
 
 // One level: out[j] = in[2j] + in[2j+1] for j < n_pairs = (total[0] >> shift) / 2; total[1 + shift] = B of the level.  FIRST: in[k] = +-table[entries[k]]
-// (bit 31 = negate, AFF_PAD_ENTRY = infinity).  A warp owns 32 * B consecutive pairs, lane l the pairs
-// warp_base + 32 i + l: consecutive lanes touch consecutive points, so the loads / stores of the upper levels and of
-// the entry list are contiguous per warp.
+// (bit 31 = negate, AFF_PAD_ENTRY = infinity).  Every lane does up to B additions; consecutive lanes touch consecutive
+// pairs, so the loads / stores of the upper levels and of the entry list are contiguous per warp.
 //
 // Everything the two loops consume arrives through cp.async (LDGSTS) into shared memory, issued iterations ahead:
 // the table rows, the entries that address them, and -- on the way back -- the prefix products the forward pass left
-// in `pre_g` ([warp][i][lane], global scratch).  A plain load would be waited for at the next CALL (the field products
+// in `pre_g` ([row][quad][lane], global scratch).  A plain load would be waited for at the next CALL (the field products
 // are calls, ec.cuh), i.e. its whole latency exposed once per pair; an asynchronous copy is only waited for when its
 // data is read.  One commit group per iteration:
 //   forward   G_i = { x_P, x_Q of pair i + 2;  entries of pair i + 4 },        wait_group 1 at the top of iteration i
@@ -125,12 +124,18 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
     const uint32_t n_pairs = (total[0] >> shift) >> 1;
     const uint32_t B = min(total[1 + shift], AFF_B_MAX);  // plan of this level (table_pad_offsets)
     const uint32_t warp = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const uint32_t warp_base = warp * (32u * B);
-    if (warp_base >= n_pairs) return;  // whole warp
+    // W warps share the level; in its i-th iteration warp w takes the 32 pairs of row i W + w, so one iteration of
+    // all warps together sweeps one contiguous stretch of the arrays (entries, upper-level points, prefix products,
+    // results) instead of W streams a warp's whole share apart
+    const uint32_t W = (n_pairs + 32u * B - 1) / (32u * B);
+    if (warp >= W) return;  // whole warp
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t j0 = warp_base + lane;
-    const int m = j0 < n_pairs ? (int)min(B, (n_pairs - j0 + 31) / 32) : 0;
-    F* my_pre = pre_g + (size_t)warp * (32u * B) + lane;  // pre[i] at my_pre[32 i]
+    const uint32_t rows = lane < n_pairs ? (n_pairs - lane + 31) / 32 : 0;  // rows r with pair 32 r + lane in range
+    const int m = rows > warp ? (int)min(B, (rows - warp + W - 1) / W) : 0;
+    auto pair_of = [&](int i) { return ((uint32_t)i * W + warp) * 32u + lane; };
+    // prefix product i of this lane: quad q at pre_q[((i W + w) QX + q) 32 + lane] -- a warp's 16-byte stores coalesce
+    uint4* pre_q = reinterpret_cast<uint4*>(pre_g) + lane;
+    auto pre_quad = [&](int i, int q) { return pre_q + (((size_t)i * W + warp) * (sizeof(F) / 16) + q) * 32; };
 
     auto cp16 = [](uint4* dst, const uint4* src) {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
         if constexpr (FIRST) {
             if (i >= 0 && i < m)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(ering + (i & 7) * 128)),
-                             "l"(reinterpret_cast<const uint2*>(entries) + (j0 + 32u * (uint32_t)i)));
+                             "l"(reinterpret_cast<const uint2*>(entries) + pair_of(i)));
         }
     };
     auto e_get = [&](int i) -> uint2 {
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
     };
     auto point_ptr = [&](int i, int which, uint32_t e) -> const Affine<F>* {
         if constexpr (FIRST) return in + (e & 0x7fffffffu);
-        else return in + 2 * (size_t)(j0 + 32u * (uint32_t)i) + which;
+        else return in + 2 * (size_t)pair_of(i) + which;
     };
     // cp.async nq quads of the point into staging quads dst0...; a padding entry stages zeros
     auto stage_point = [&](const Affine<F>* p, bool pad, int nq, int dst0) {
@@ -208,13 +213,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
             F d = fp_sub(xq, xp);
             if (xp.is_zero() || xq.is_zero() || d.is_zero()) {
                 const Affine<F> p = load_full(i, 0, ecur.x), q = load_full(i, 1, ecur.y);
-                aff_classify_slow(p, q, d);
+                F ds;  // the callee takes references: keep what it touches local to this branch, or `d` lives on the stack
+                aff_classify_slow(p, q, ds);
+                d = ds;
             }
             acc = CallOps::mul(acc, d);
-            uint4* dst = reinterpret_cast<uint4*>(my_pre + 32 * i);
             const uint4* src = reinterpret_cast<const uint4*>(&acc);
 #pragma unroll
-            for (int qq = 0; qq < QX; qq++) dst[qq] = src[qq];
+            for (int qq = 0; qq < QX; qq++) *pre_quad(i, qq) = src[qq];
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
@@ -228,9 +234,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
                 stage_point(point_ptr(i, 0, e.x), e.x == AFF_PAD_ENTRY, Q, 0);
                 stage_point(point_ptr(i, 1, e.y), e.y == AFF_PAD_ENTRY, Q, Q);
                 if (i > 0) {
-                    const uint4* src = reinterpret_cast<const uint4*>(my_pre + 32 * (i - 1));
 #pragma unroll
-                    for (int qq = 0; qq < QX; qq++) cp16(my + (2 * Q + qq) * 128, src + qq);
+                    for (int qq = 0; qq < QX; qq++) cp16(my + (2 * Q + qq) * 128, pre_quad(i - 1, qq));
                 }
             }
         };
@@ -261,7 +266,10 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
             F num = fp_sub(q.y, p.y);
             uint32_t kind = AFF_ADD;
             if (p.x.is_zero() || q.x.is_zero() || d.is_zero()) {
-                kind = aff_classify_slow(p, q, d);
+                const Affine<F> pc = p, qc = q;  // copies for the by-reference callee: p, q, d stay in registers on the fast path
+                F ds;
+                kind = aff_classify_slow(pc, qc, ds);
+                d = ds;
                 if (kind == AFF_DBL) {
                     const F xx = CallOps::sqr(p.x);
                     num = fp_add(fp_dbl(xx), xx);
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
             } else {
                 r = kind == AFF_COPY_P ? p : (kind == AFF_COPY_Q ? q : Affine<F>::inf());
             }
-            uint4* dst = reinterpret_cast<uint4*>(out + (j0 + 32u * (uint32_t)i));
+            uint4* dst = reinterpret_cast<uint4*>(out + pair_of(i));
             const uint4* src = reinterpret_cast<const uint4*>(&r);
 #pragma unroll
             for (int qq = 0; qq < Q; qq++) dst[qq] = src[qq];

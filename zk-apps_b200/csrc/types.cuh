@@ -18,6 +18,7 @@ struct b200zk_bases {
     // of one table entry per non-zero signed digit: no buckets, no sort, no bucket reduction.
     void* d_table = nullptr;
     uint32_t mult = 0;
+    int table_glv = 0;  // the table's windows cover GLV half scalars (GLV_BITS): k1 rows as they are, phi applied to the k2 sum
 };
 
 struct b200zk_r1cs {
