@@ -257,3 +257,38 @@ def test_digit_table_affine_levels(ctx, group, n, c, levels, b):
     finally:
         ctx.set_option(opt, 13)
         ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 96)
+
+
+@pytest.mark.parametrize("group,n,c,glv", [(1, 3000, 4, 1), (1, 2500, 5, 0), (2, 700, 3, 1)])
+def test_plain_bases_affine_levels(ctx, group, n, c, glv, monkeypatch):
+    """Affine levels in front of the bucket accumulation of a plain-bases MSM (buckets padded to 2^levels entries in the
+    sorted list): same bytes as with the levels off, with and without GLV, incl. bases at infinity, repeated bases
+    (doublings inside a bucket) and P / -P pairs."""
+    monkeypatch.setenv("B200ZK_MSM_C", str(c))          # few, large buckets so that the levels apply at this size
+    cv, enc, dec, pt = CURVES[group]
+    ks = util.rand_fr_bytes_fast(1300 + n, n)
+    pts = ctx.fixed_base_mul(group, ks).copy()
+    pts[5 * pt:6 * pt] = 0
+    pts[10 * pt:11 * pt] = pts[11 * pt:12 * pt]                    # a repeated base
+    neg = dec(pts[20 * pt:21 * pt])[0]
+    pts[21 * pt:22 * pt] = enc([cv.neg(neg)])                       # and an opposite pair
+    ss = util.rand_fr_bytes_fast(1400 + n, n).reshape(n, 32).copy()
+    ss[10] = ss[11]; ss[20] = ss[21]
+    h = z.VariableBaseMSM.Bases(ctx, group, pts)
+    try:
+        ctx.set_option("msm_glv", glv)
+        ctx.set_option("msm_affine_levels", 0)
+        want, want_inf = h.msm(ss.reshape(-1), n=n)
+        ctx.set_option("msm_affine_levels", 4); ctx.set_option("msm_affine_min_entries", 0); ctx.set_option("msm_affine_b", 16)
+        got, got_inf = h.msm(ss.reshape(-1), n=n)
+        assert bytes(got) == bytes(want) and list(got_inf) == list(want_inf)
+        same = util.scalars_array([7] * n)                           # all-equal scalars: one bucket per window takes everything
+        ctx.set_option("msm_affine_levels", 0)
+        want2, _ = h.msm(same, n=n)
+        ctx.set_option("msm_affine_levels", 4)
+        got2, _ = h.msm(same, n=n)
+        assert bytes(got2) == bytes(want2)
+    finally:
+        ctx.set_option("msm_glv", 1); ctx.set_option("msm_affine_levels", 4)
+        ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 96)
+        h.free()

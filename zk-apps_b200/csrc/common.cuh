@@ -53,6 +53,8 @@ struct b200zk_ctx {
     // full digit tables: rounds of pairwise batched-affine additions (csrc/msm_affine.cuh) before the XYZZ running sums
     int msm_affine_levels = 4;                             // b200zk_set_option("msm_affine_levels"): 0 = off
     long long msm_affine_min_entries = 1ll << 22;          // ... only for batches with at least this many table entries
+    long long msm_affine_min_entries_buckets = 1ll << 26;  // ... and, over plain bases (bucket method), for MSMs this large
+                                                           // (measured: a gain from 2^22 points, a loss at 2^20)
     int msm_affine_b = 96;                                 // target additions per lane sharing one inversion per warp (the device plan rounds it to whole waves)
     std::string last_error;
     std::map<std::string, b200zk::DeviceBuf> scratch;      // named, grow-only

@@ -20,7 +20,10 @@ int b200zk_init(int device, b200zk_ctx** out) {
     ctx->device = device;
     // experiment / test overrides of the affine-level defaults (b200zk_set_option has the same knobs)
     if (const char* e = getenv("B200ZK_AFFINE_LEVELS")) ctx->msm_affine_levels = std::max(0, std::min(8, atoi(e)));
-    if (const char* e = getenv("B200ZK_AFFINE_MIN_ENTRIES")) ctx->msm_affine_min_entries = std::max(0ll, atoll(e));
+    if (const char* e = getenv("B200ZK_AFFINE_MIN_ENTRIES")) {
+        ctx->msm_affine_min_entries = std::max(0ll, atoll(e));
+        ctx->msm_affine_min_entries_buckets = ctx->msm_affine_min_entries ? std::max(ctx->msm_affine_min_entries, 1ll << 26) : 0;
+    }
     if (const char* e = getenv("B200ZK_AFFINE_B")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 1024) ctx->msm_affine_b = v;
@@ -101,6 +104,7 @@ int b200zk_set_option(b200zk_ctx* ctx, const char* name, int value) {
     if (strcmp(name, "msm_affine_min_entries") == 0) {  // smaller batches keep the XYZZ running sums only
         if (value < 0) return fail(ctx, B200ZK_ERR_BAD_ARG, "msm_affine_min_entries must be >= 0");
         ctx->msm_affine_min_entries = value;
+        ctx->msm_affine_min_entries_buckets = value ? std::max<long long>(value, 1ll << 26) : 0;   // 0 = always (tests)
         return B200ZK_OK;
     }
     if (strcmp(name, "msm_affine_b") == 0) {  // additions per lane that share one inversion per warp

@@ -55,6 +55,10 @@ uint32_t pick_window(size_t n, bool precomp, bool glv) {
         int v = atoi(e);
         if (v >= 2 && v <= 22) return (uint32_t)v;
     }
+    // GLV half scalars over plain bases: measured (profiles/r02_msm_window_sweep.log, G1 2^16...2^26, G2 2^18).  The
+    // operation-count model below does not see that the top window of a 128-bit half scalar is nearly empty at c = 16
+    // (bit 128 up) and badly skewed at c = 17, 18 (a few hundred huge buckets), nor what the affine levels save.
+    if (glv && !precomp) return n < (1u << 21) ? 15u : n < (1u << 25) ? 16u : 19u;
     const uint32_t bits = glv ? GLV_BITS : 256;
     double best = 1e300;
     uint32_t best_c = 3;
@@ -828,6 +832,35 @@ __global__ void table_pad_offsets(const uint32_t* __restrict__ off, size_t n, si
     }
 }
 
+// ---- affine levels over the bucket-sorted entry list of plain bases: every bucket is padded to a multiple of 2^levels
+// entries (the sorted array is pre-filled with AFF_PAD_ENTRY), so pairs never straddle a bucket at any level
+__global__ void pad_counts(uint32_t* __restrict__ counts, uint32_t n_keys, uint32_t levels) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t mask = (1u << levels) - 1;
+    if (key < n_keys) counts[key] = (counts[key] + mask) & ~mask;
+}
+// plan[0] = padded entry count, plan[1 + lv] = additions per lane of level lv (whole waves, as in table_pad_offsets)
+__global__ void bucket_affine_plan(const uint32_t* __restrict__ offsets, uint32_t n_keys, uint32_t levels, uint32_t B0,
+                                   uint32_t b_min, uint32_t lanes_per_wave, uint32_t* __restrict__ plan) {
+    const uint32_t total = offsets[n_keys];
+    plan[0] = total;
+    for (uint32_t lv = 0; lv < levels; lv++) {
+        const uint64_t pairs = total >> (lv + 1), per_wave = (uint64_t)lanes_per_wave * B0;
+        uint32_t B = B0;
+        if (lanes_per_wave) {
+            uint64_t waves = (pairs + per_wave / 2) / per_wave;
+            if (waves == 0) waves = 1;
+            const uint64_t lanes = lanes_per_wave * waves;
+            B = (uint32_t)((pairs + lanes - 1) / lanes);
+        }
+        plan[1 + lv] = B < b_min ? b_min : B;
+    }
+}
+__global__ void shift_offsets(uint32_t* __restrict__ offsets, uint32_t count, uint32_t levels) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) offsets[i] >>= levels;
+}
+
 // one CTA per proof: sum of the partial sums its runs left (or the single whole sum), log-depth
 template <class F>
 __global__ void __launch_bounds__(128) msm_sum_partials(const uint32_t* __restrict__ toff, const XYZZ<F>* __restrict__ partials,
@@ -942,19 +975,79 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     B200ZK_TRY(scratch(ctx, "msm_counts", ((size_t)n_keys + 1) * 4, &d_counts, slot));
     B200ZK_TRY(scratch(ctx, "msm_offsets", ((size_t)n_keys + 1) * 4, &d_offsets, slot));
     B200ZK_TRY(scratch(ctx, "msm_cursor", ((size_t)n_keys + 1) * 4, &d_cursor, slot));
-    B200ZK_TRY(scratch(ctx, "msm_sorted", ((size_t)max_entries + (pl.table ? batch * 256 : 0)) * 4, &d_sorted, slot));   // + affine-level padding
+    B200ZK_TRY(scratch(ctx, "msm_sorted", ((size_t)max_entries + (pl.table ? batch * 256 : (size_t)n_keys * 16)) * 4, &d_sorted, slot));   // + affine-level padding
     B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_buckets_g1" : "msm_buckets_g2",
                        (size_t)n_keys * sizeof(XYZZ<F>), &d_buckets, slot));
 
     const size_t total = n * batch;
     // ---- affine levels (msm_affine.cuh): K rounds of pairwise batched-affine additions before the XYZZ running sums
     uint32_t aff_levels = 0;
-    if (pl.table && ctx->msm_affine_levels > 0 && max_entries >= (uint64_t)ctx->msm_affine_min_entries)
+    if (ctx->msm_affine_levels > 0 &&
+        max_entries >= (uint64_t)(pl.table ? ctx->msm_affine_min_entries : ctx->msm_affine_min_entries_buckets)) {
         aff_levels = (uint32_t)ctx->msm_affine_levels;
-    const uint64_t padded_entries = max_entries + (aff_levels ? (uint64_t)batch << aff_levels : 0);
+        if (!pl.table) {
+            // buckets: padding costs (2^levels - 1) / 2 entries per bucket on average -> levels <= log2(mean bucket / 8);
+            // and the levels need room (half the entries as points, twice): skipped when the device is that full
+            const uint64_t mean = max_entries / std::max<uint64_t>(1, n_keys64);
+            aff_levels = std::min(aff_levels, 4u);
+            while (aff_levels > 0 && (8ull << aff_levels) > mean) aff_levels--;
+            size_t free_b = 0, total_b = 0;
+            const uint64_t need = (max_entries + (n_keys64 << aff_levels)) * (sizeof(Affine<F>) * 3 / 4 + sizeof(F) / 2 + 8);
+            if (aff_levels && (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + (need >> 3))) {
+                // unless this slot already holds buffers that large from an earlier call
+                auto it = ctx->scratch.find(std::string(sizeof(F) == sizeof(Fq) ? "msm_aff_a_g1" : "msm_aff_a_g2") +
+                                            (slot > 0 ? "#" + std::to_string(slot) : ctx->lane ? "@" + std::to_string(ctx->lane) : ""));
+                if (it == ctx->scratch.end() || it->second.bytes < (max_entries / 2) * sizeof(Affine<F>)) aff_levels = 0;
+            }
+        }
+    }
+    const uint64_t padded_entries = max_entries + (aff_levels ? (pl.table ? (uint64_t)batch : n_keys64) << aff_levels : 0);
     if (padded_entries >= (1ull << 32)) return fail(ctx, B200ZK_ERR_BAD_LEN, "MSM too large for 32-bit entry offsets; split the batch");
     const Affine<F>* acc_bases = (const Affine<F>*)(pl.table ? h->d_table : h->d_points);
     const uint32_t* acc_entries = (const uint32_t*)d_sorted;
+    uint32_t acc_n_split = pl.glv ? (uint32_t)n : 0x80000000u;
+    // the levels: entries (d_sorted) over `first` / `first2` -> A (half the entries) -> B (a quarter) -> A ...; d_plan[0] =
+    // padded entry count, d_plan[1 + lv] = additions per lane of level lv (both fixed on the device)
+    auto run_levels = [&](const Affine<F>* first, const Affine<F>* first2, uint32_t n_split, const uint32_t* d_plan_aff) -> int {
+        ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_affine_g1" : "msm_affine_g2", st);
+        void *d_a, *d_b, *d_pre;
+        B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_a_g1" : "msm_aff_a_g2",
+                           (size_t)(padded_entries / 2 + 1) * sizeof(Affine<F>), &d_a, slot));
+        B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_b_g1" : "msm_aff_b_g2",
+                           (size_t)(padded_entries / 4 + 1) * sizeof(Affine<F>), &d_b, slot));
+        // prefix products of the forward pass, [row][quad][lane]: one field element per pair of the largest level
+        // (+ slack: the last rows are addressed whole)
+        B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_pre_g1" : "msm_aff_pre_g2",
+                           ((size_t)(padded_entries / 2) + 32 * (size_t)AFF_B_MAX) * sizeof(F), &d_pre, slot));
+        const Affine<F>* src = first;
+        for (uint32_t lv = 0; lv < aff_levels; lv++) {
+            Affine<F>* dst = (Affine<F>*)((lv & 1) ? d_b : d_a);
+            const uint64_t max_pairs = padded_entries >> (lv + 1);
+            // the grid covers the worst case of the plan (B >= 2/3 B0 with several waves, one wave otherwise); warps
+            // beyond the real count exit at once
+            const size_t B0 = std::max<size_t>(AFF_B_MIN, (size_t)ctx->msm_affine_b);
+            const size_t wave_warps = (size_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3 : 2) * 4;
+            const unsigned grid = div_up(std::max(wave_warps, (size_t)div_up(max_pairs * 3, 64 * B0)) + 1, 4);
+            constexpr int OCC = sizeof(F) == sizeof(Fq) ? 3 : 2;
+            auto kern = lv == 0 ? msm_affine_level<F, true, OCC> : msm_affine_level<F, false, OCC>;
+            const size_t smem = aff_smem_bytes<F>(lv == 0);
+            if (smem > 48 * 1024) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 128, smem, st>>>(src, first2, n_split, lv == 0 ? (const uint32_t*)d_sorted : nullptr, d_plan_aff, lv, dst,
+                                          (F*)d_pre);
+            B200ZK_TRY(check_launch(ctx, "msm_affine_level"));
+            src = dst;
+        }
+        acc_bases = src;
+        acc_entries = nullptr;
+        acc_n_split = 0x80000000u;
+        if (ctx->prof_enabled && !ctx->concurrency) {  // work counter: additions done by the affine levels
+            uint32_t padded = 0;
+            B200ZK_CUDA(ctx, cudaMemcpyAsync(&padded, d_plan_aff, 4, cudaMemcpyDeviceToHost, st));
+            B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_affine_adds_g1" : "msm_affine_adds_g2"] += padded - (padded >> aff_levels);
+        }
+        return B200ZK_OK;
+    };
     if (pl.table) {
         // entries in scalar order, proof after proof: per-scalar digit counts -> scan -> entries; no sort, no atomics
         void *d_cnt, *d_off, *d_pstart = nullptr;
@@ -983,57 +1076,35 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
                                                               (uint32_t*)d_sorted);
             B200ZK_TRY(check_launch(ctx, "table_entries"));
         }
-        if (aff_levels) {
-            // ping-pong: level 0 -> A (half the entries), level 1 -> B (a quarter), level 2 -> A, ...
-            ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_affine_g1" : "msm_affine_g2", st);
-            void *d_a, *d_b;
-            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_a_g1" : "msm_aff_a_g2",
-                               (size_t)(padded_entries / 2 + 1) * sizeof(Affine<F>), &d_a, slot));
-            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_b_g1" : "msm_aff_b_g2",
-                               (size_t)(padded_entries / 4 + 1) * sizeof(Affine<F>), &d_b, slot));
-            const uint32_t* d_total = (const uint32_t*)d_pstart + batch;
-            // prefix products of the forward pass, [row][quad][lane]: one field element per pair of the largest level
-            // (+ slack: the last rows are addressed whole)
-            void* d_pre;
-            B200ZK_TRY(scratch(ctx, sizeof(F) == sizeof(Fq) ? "msm_aff_pre_g1" : "msm_aff_pre_g2",
-                               ((size_t)(padded_entries / 2) + 32 * (size_t)AFF_B_MAX) * sizeof(F), &d_pre, slot));
-            const Affine<F>* src = (const Affine<F>*)h->d_table;
-            for (uint32_t lv = 0; lv < aff_levels; lv++) {
-                Affine<F>* dst = (Affine<F>*)((lv & 1) ? d_b : d_a);
-                const uint64_t max_pairs = padded_entries >> (lv + 1);
-                // the grid covers the worst case of the plan (B >= 2/3 B0 with several waves, one wave otherwise); warps
-                // beyond the real count exit at once
-                const size_t B0 = std::max<size_t>(AFF_B_MIN, (size_t)ctx->msm_affine_b);
-                const size_t wave_warps = (size_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3 : 2) * 4;
-                const unsigned grid = div_up(std::max(wave_warps, (size_t)div_up(max_pairs * 3, 64 * B0)) + 1, 4);
-                constexpr int OCC = sizeof(F) == sizeof(Fq) ? 3 : 2;
-                auto kern = lv == 0 ? msm_affine_level<F, true, OCC> : msm_affine_level<F, false, OCC>;
-                const size_t smem = aff_smem_bytes<F>(lv == 0);
-                if (smem > 48 * 1024) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<grid, 128, smem, st>>>(src, lv == 0 ? (const uint32_t*)d_sorted : nullptr, d_total, lv, dst, (F*)d_pre);
-                B200ZK_TRY(check_launch(ctx, "msm_affine_level"));
-                src = dst;
-            }
-            acc_bases = src;
-            acc_entries = nullptr;
-            if (ctx->prof_enabled && !ctx->concurrency) {  // work counter: additions done by the affine levels
-                uint32_t padded = 0;
-                B200ZK_CUDA(ctx, cudaMemcpyAsync(&padded, d_total, 4, cudaMemcpyDeviceToHost, st));
-                B200ZK_CUDA(ctx, cudaStreamSynchronize(st));
-                ctx->stats[sizeof(F) == sizeof(Fq) ? "msm_affine_adds_g1" : "msm_affine_adds_g2"] += padded - (padded >> aff_levels);
-            }
-        }
+        if (aff_levels) B200ZK_TRY(run_levels((const Affine<F>*)h->d_table, nullptr, 0x80000000u, (const uint32_t*)d_pstart + batch));
     } else {
         B200ZK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, ((size_t)n_keys + 1) * 4, st));
         ProfScope ps(ctx, "msm_sort", st);
         msm_count<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl, h->d_skip,
                                                                (uint32_t*)d_counts);
         B200ZK_TRY(check_launch(ctx, "msm_count"));
+        if (aff_levels) {  // bucket starts on multiples of 2^levels, the gaps hold the padding entry
+            pad_counts<<<div_up(n_keys, 256), 256, 0, st>>>((uint32_t*)d_counts, n_keys, aff_levels);
+            B200ZK_TRY(check_launch(ctx, "pad_counts"));
+            B200ZK_CUDA(ctx, cudaMemsetAsync(d_sorted, 0xff, (size_t)padded_entries * 4, st));
+        }
         B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_counts, n_keys, (uint32_t*)d_offsets));
         B200ZK_CUDA(ctx, cudaMemcpyAsync(d_cursor, d_offsets, (size_t)n_keys * 4, cudaMemcpyDeviceToDevice, st));
         msm_scatter<<<div_up(total, 256), 256, 0, st>>>(d_scalars, n, stride, batch, mont ? 1 : 0, pl, h->d_skip,
                                                                  (uint32_t*)d_cursor, (uint32_t*)d_sorted);
         B200ZK_TRY(check_launch(ctx, "msm_scatter"));
+    }
+    if (aff_levels && !pl.table) {
+        void* d_aplan;
+        B200ZK_TRY(scratch(ctx, "msm_aff_plan", 16 * 4, &d_aplan, slot));
+        static const int bal_env = getenv("B200ZK_AFFINE_BALANCE") ? atoi(getenv("B200ZK_AFFINE_BALANCE")) : 1;
+        const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3u : 2u) * 128u;
+        bucket_affine_plan<<<1, 1, 0, st>>>((const uint32_t*)d_offsets, n_keys, aff_levels, (uint32_t)ctx->msm_affine_b, AFF_B_MIN,
+                                            bal_env ? aff_lanes : 0u, (uint32_t*)d_aplan);
+        B200ZK_TRY(check_launch(ctx, "bucket_affine_plan"));
+        B200ZK_TRY(run_levels((const Affine<F>*)h->d_points, d_phi, pl.glv ? (uint32_t)n : 0x80000000u, (const uint32_t*)d_aplan));
+        shift_offsets<<<div_up((size_t)n_keys + 1, 256), 256, 0, st>>>((uint32_t*)d_offsets, n_keys + 1, aff_levels);
+        B200ZK_TRY(check_launch(ctx, "shift_offsets"));
     }
     // runs of L = 2^log_tl entries; smaller L when the problem is small, to keep the SMs busy
     void *d_tcount, *d_toff, *d_partials, *d_big;
@@ -1108,7 +1179,7 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         static const int smem_kb = getenv("B200ZK_ACC_SMEM_KB") ? atoi(getenv("B200ZK_ACC_SMEM_KB")) : 0;
         if (smem_kb > 0) B200ZK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
         kern<<<div_up(max_runs, acc_threads), acc_threads, (size_t)smem_kb * 1024, st>>>(
-            acc_bases, d_phi, pl.glv ? (uint32_t)n : 0x80000000u,
+            acc_bases, d_phi, acc_n_split,
             (const uint32_t*)d_offsets, acc_entries,
             (const uint32_t*)d_toff, n_keys, (const RunPlan*)d_plan, (XYZZ<F>*)d_buckets, (XYZZ<F>*)d_partials);
         B200ZK_TRY(check_launch(ctx, "msm_accumulate"));

@@ -110,6 +110,7 @@ constexpr size_t aff_smem_bytes(bool first) {
 //   backward  G_i = { P, Q of pair i - 1;  pre[i - 2];  entries of pair i - 3 }, wait_group 0
 template <class F, bool FIRST, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine<F>* __restrict__ in,
+                                                                    const Affine<F>* __restrict__ in2, uint32_t n_split,
                                                                     const uint32_t* __restrict__ entries,
                                                                     const uint32_t* __restrict__ total, uint32_t shift,
                                                                     Affine<F>* __restrict__ out, F* __restrict__ pre_g) {
@@ -152,8 +153,10 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) msm_affine_level(const Affine
         else return make_uint2(0, 0);
     };
     auto point_ptr = [&](int i, int which, uint32_t e) -> const Affine<F>* {
-        if constexpr (FIRST) return in + (e & 0x7fffffffu);
-        else return in + 2 * (size_t)pair_of(i) + which;
+        if constexpr (FIRST) {  // entries below n_split index `in`, the others `in2` (the phi half of a GLV base table)
+            const uint32_t idx = e & 0x7fffffffu;
+            return idx < n_split ? in + idx : in2 + (idx - n_split);
+        } else return in + 2 * (size_t)pair_of(i) + which;
     };
     // cp.async nq quads of the point into staging quads dst0...; a padding entry stages zeros
     auto stage_point = [&](const Affine<F>* p, bool pad, int nq, int dst0) {
