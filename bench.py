@@ -264,6 +264,9 @@ def rand_scalars_device(torch, m: int, seed: int, device):
     g.manual_seed(seed)
     t = torch.randint(0, 256, (m, 32), dtype=torch.uint8, device=device, generator=g)
     t[:, 31] &= 0x3F
+    # torch fills the tensor on ITS stream; the library's streams are non-blocking, so without this a call that
+    # reads the pointer right away can see a partly written buffer (observed: bases built from half-filled scalars)
+    torch.cuda.synchronize()
     return t
 
 

@@ -73,10 +73,16 @@ int b200zk_sync(b200zk_ctx* ctx);
  * streams; 0 serialises everything on the ctx stream (used for per-kernel profiling).
  * "msm_parts" (default 0 = automatic: 4 from 2^23 points, else 1): number of window groups a single
  * MSM over plain (not precomputed) bases is cut into, each a pass of the pipeline on its own stream.
- * "table_c_g1" (default 12) / "table_c_g2" (default 12): window of full digit tables (precompute level 2) built after
+ * "table_c_g1" (default 13) / "table_c_g2" (default 13): window of full digit tables (precompute level 2) built after
  * the call.
+ * "msm_affine_levels" (default 4; 0 = off): rounds of pairwise batched-affine additions (5M + 1S each, one shared
+ * inversion per warp) in front of the running sums of an MSM -- over digit tables for batches with at least
+ * "msm_affine_min_entries" table entries (default 2^22; 0 = always), over plain bases (bucket method) from 2^26 entries;
+ * "msm_affine_b" (default 96): target additions per lane that share one inversion.  Same result bytes with any setting.
  * "msm_glv" (default 1): MSMs (G1 and G2) over plain bases split every scalar as k1 + k2*lambda (two non-negative
- * 128/129-bit halves, phi(x, y) = (beta x, y)); 0 keeps full-length scalars.  Same result bytes either way FOR BASES
+ * 128/129-bit halves, phi(x, y) = (beta x, y)), and full digit tables built while it is on cover the half scalars
+ * (130 instead of 256 bits of windows; the k2 rows are summed as they are and phi is applied once to their sum);
+ * 0 keeps full-length scalars.  Same result bytes either way FOR BASES
  * IN THE ORDER-r SUBGROUP (k*P = k1*P + k2*phi(P) needs phi(P) = lambda*P, which holds on G1/G2 only: for the
  * order-3 point (0, 2) the two paths differ).  Every proving-key query and every ark `G1Affine`/`G2Affine` that
  * went through checked deserialisation is in the subgroup; for bases of unknown origin call
@@ -172,10 +178,11 @@ int b200zk_msm_g2(b200zk_ctx* ctx, const uint8_t* bases, const uint8_t* inf_flag
                   const uint8_t* scalars, size_t n, uint8_t out_affine[192], uint8_t* out_is_inf);
 /* group: 1 = G1, 2 = G2.  precompute: 0 = plain bases (GLV at MSM time); 1 = also the window multiples 2^(c w) P_i
  * (memory x windows; all windows then share one bucket set and nothing is left to combine); 2 = the FULL DIGIT TABLE
- * (m + 1) 2^(c w) P_i for every m < 2^(c-1), resident in HBM (n * ceil(256/c) * 2^(c-1) points: 24 GB for a G1 query
- * of 5,653 points at c = 12 -- sized for the 180 GB of a B200; window from the options "table_c_g1" (default 12) /
- * "table_c_g2" (default 12) at the time of this call).  An MSM over a full table is one mixed addition per non-zero
- * signed digit and nothing else: no buckets, no sort, no bucket reduction.  Same result bytes at every level. */
+ * (m + 1) 2^(c w) P_i for every m < 2^(c-1), resident in HBM (n * ceil(130/c) * 2^(c-1) points over GLV half scalars,
+ * ceil(256/c) windows with msm_glv = 0: 22 GB for a G1 query of 5,653 points at c = 13 -- sized for the 180 GB of a
+ * B200; window from the options "table_c_g1" / "table_c_g2" (default 13) at the time of this call).  An MSM over a
+ * full table is one addition per non-zero signed digit and nothing else: no buckets, no sort, no bucket reduction.
+ * Same result bytes at every level. */
 int b200zk_bases_upload(b200zk_ctx* ctx, int group, const uint8_t* bases, const uint8_t* inf_flags,
                         size_t n, int precompute, b200zk_bases** out);
 /* wrap points already in device memory (affine, library layout); the library copies them */
@@ -312,7 +319,7 @@ int b200zk_merkle_fill_update_note_inputs_device(b200zk_ctx* ctx, const b200zk_m
  * 5 x 32 B canonical LE) -- ark_groth16::generate_parameters_with_qap [recall]; fixed-base
  * multiplications run on the GPU.  vk_out (may be NULL): alpha_g1 (96) | beta_g2 (192) |
  * gamma_g2 (192) | delta_g2 (192) | gamma_abc_g1 (num_inputs * 96).
- * precompute: 0 / 1 / 2 as in b200zk_bases_upload, applied to every query (2 = full digit tables: ~158 GB (147 GiB) for the
+ * precompute: 0 / 1 / 2 as in b200zk_bases_upload, applied to every query (2 = full digit tables: ~143 GB (133 GiB) for the
  * withdraw key at the default windows, built once in a few seconds).
  * b200zk_groth16_prove_batch = create_proof_with_reduction(circuit, pk, r, s) for `batch` full
  * assignments (batch*num_vars*32 B Montgomery, host or device); r, s: batch*32 B canonical LE.

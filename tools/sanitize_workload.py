@@ -11,6 +11,8 @@ from oracle.pyref import relations as rel
 from tests import util
 
 ctx = z.Context(0)
+ctx.set_option("msm_affine_min_entries", 0)                   # the batched-affine levels at every size (msm_affine.cuh)
+ctx.set_option("msm_affine_b", 8)
 n = 1 << 10
 for group in (1, 2):
     pts = ctx.fixed_base_mul(group, util.rand_fr_bytes_fast(1, n))
@@ -20,6 +22,9 @@ for group in (1, 2):
     ctx.set_option("msm_glv", 0)
     assert z.VariableBaseMSM.msm_bigint(ctx, group, pts, ss)[0] == want
     ctx.set_option("msm_glv", 1)
+    os.environ["B200ZK_MSM_C"] = "4"                          # few large buckets: the affine levels of the bucket path apply
+    assert z.VariableBaseMSM.msm_bigint(ctx, group, pts, ss)[0] == want
+    del os.environ["B200ZK_MSM_C"]
     for level in (1, 2):
         ctx.set_option("table_c_g1", 5); ctx.set_option("table_c_g2", 4)
         h = z.VariableBaseMSM.Bases(ctx, group, pts, precompute=level)

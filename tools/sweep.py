@@ -19,7 +19,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--out", default="gpurun_out/sweep.json")
 args = ap.parse_args()
 ctx = z.Context(0)
-peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_int_peaks.json")))
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_int_peaks.json")))
 res = {"msm": [], "ntt": [], "host_threads": None}
 
 

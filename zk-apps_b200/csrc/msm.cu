@@ -985,6 +985,8 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     if (ctx->msm_affine_levels > 0 &&
         max_entries >= (uint64_t)(pl.table ? ctx->msm_affine_min_entries : ctx->msm_affine_min_entries_buckets)) {
         aff_levels = (uint32_t)ctx->msm_affine_levels;
+        static const int buckets_env = getenv("B200ZK_AFFINE_BUCKETS") ? atoi(getenv("B200ZK_AFFINE_BUCKETS")) : 1;
+        if (!pl.table && !buckets_env) aff_levels = 0;
         if (!pl.table) {
             // buckets: padding costs (2^levels - 1) / 2 entries per bucket on average -> levels <= log2(mean bucket / 8);
             // and the levels need room (half the entries as points, twice): skipped when the device is that full
@@ -1008,6 +1010,9 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
     uint32_t acc_n_split = pl.glv ? (uint32_t)n : 0x80000000u;
     // the levels: entries (d_sorted) over `first` / `first2` -> A (half the entries) -> B (a quarter) -> A ...; d_plan[0] =
     // padded entry count, d_plan[1 + lv] = additions per lane of level lv (both fixed on the device)
+    // resident CTAs per SM of the level kernels (164 / 255 registers).  Measured: one more CTA per SM (128 / 168
+    // registers, 0.4 / 1 KB of spills per thread) is slower, G1 15.5 -> 16.2 ms, G2 6.8 -> 8.9 ms per step
+    const int aff_occ = sizeof(F) == sizeof(Fq) ? 3 : 2;
     auto run_levels = [&](const Affine<F>* first, const Affine<F>* first2, uint32_t n_split, const uint32_t* d_plan_aff) -> int {
         ProfScope ps(ctx, sizeof(F) == sizeof(Fq) ? "msm_affine_g1" : "msm_affine_g2", st);
         void *d_a, *d_b, *d_pre;
@@ -1026,7 +1031,7 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             // the grid covers the worst case of the plan (B >= 2/3 B0 with several waves, one wave otherwise); warps
             // beyond the real count exit at once
             const size_t B0 = std::max<size_t>(AFF_B_MIN, (size_t)ctx->msm_affine_b);
-            const size_t wave_warps = (size_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3 : 2) * 4;
+            const size_t wave_warps = (size_t)ctx->sm_count * aff_occ * 4;
             const unsigned grid = div_up(std::max(wave_warps, (size_t)div_up(max_pairs * 3, 64 * B0)) + 1, 4);
             constexpr int OCC = sizeof(F) == sizeof(Fq) ? 3 : 2;
             auto kern = lv == 0 ? msm_affine_level<F, true, OCC> : msm_affine_level<F, false, OCC>;
@@ -1062,7 +1067,7 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
             B200ZK_TRY(exclusive_scan(ctx, st, slot, (const uint32_t*)d_cnt, total, (uint32_t*)d_off));
             if (aff_levels) {
                 static const int bal_env = getenv("B200ZK_AFFINE_BALANCE") ? atoi(getenv("B200ZK_AFFINE_BALANCE")) : 1;
-                const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3u : 2u) * 128u;
+                const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (uint32_t)aff_occ * 128u;
                 table_pad_offsets<<<1, SCAN_THREADS, 0, st>>>((const uint32_t*)d_off, n, batch, aff_levels, (uint32_t)ctx->msm_affine_b,
                                                               AFF_B_MIN, bal_env ? aff_lanes : 0u, (uint32_t*)d_pstart,
                                                               (uint32_t*)d_offsets);
@@ -1098,7 +1103,7 @@ int msm_part(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars, 
         void* d_aplan;
         B200ZK_TRY(scratch(ctx, "msm_aff_plan", 16 * 4, &d_aplan, slot));
         static const int bal_env = getenv("B200ZK_AFFINE_BALANCE") ? atoi(getenv("B200ZK_AFFINE_BALANCE")) : 1;
-        const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (sizeof(F) == sizeof(Fq) ? 3u : 2u) * 128u;
+        const uint32_t aff_lanes = (uint32_t)ctx->sm_count * (uint32_t)aff_occ * 128u;
         bucket_affine_plan<<<1, 1, 0, st>>>((const uint32_t*)d_offsets, n_keys, aff_levels, (uint32_t)ctx->msm_affine_b, AFF_B_MIN,
                                             bal_env ? aff_lanes : 0u, (uint32_t*)d_aplan);
         B200ZK_TRY(check_launch(ctx, "bucket_affine_plan"));
