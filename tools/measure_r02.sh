@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 [ "$1" = "notests" ] || timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r02_tests.log
 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
 python bench.py --impl reference > gpurun_out/r02_bench_ref.json 2>> gpurun_out/r02_bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r02_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu --no-extras > gpurun_out/r02_launches_bench.log 2>&1
 timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"msm_affine_level|msm_accumulate" --launch-count 6 \
   -o gpurun_out/r02_affine -f python bench.py --no-cpu --no-extras --steps 1 --warmup 1 > gpurun_out/r02_ncu_affine.log 2>&1

@@ -1,7 +1,7 @@
 #!/bin/bash
 # launch list (gpu__time_duration) of the MSM kernels of one bench step: gpurun_out/msm_launches.csv
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k regex:"msm_affine_level|msm_accumulate|msm_sum_partials" -c 200 --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k regex:"msm_affine|msm_accumulate|msm_sum_partials" -c 200 --csv \
   --log-file gpurun_out/msm_launches.csv python bench.py --no-cpu --no-extras --steps 1 --warmup 1 > gpurun_out/ncu_list.log 2>&1
 python - <<'PY'
 import csv

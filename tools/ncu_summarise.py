@@ -49,14 +49,24 @@ def launches(src, dst):
         agg[k][0] += 1
         agg[k][1] += v
     scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(unit, 1e-6)
-    tot = sum(v[1] for v in agg.values())
+    # key generation (digit tables, window multiples, fixed-base multiplications) runs once per key, outside the timed
+    # region: listed apart so that the shares are those of the proof steps
+    setup = ("table_multiples", "table_to_affine", "msm_precompute_step", "mark_infinity", "mont_conv_kernel", "fixed_base_kernel",
+             "delta_table_kernel", "apply_inf_flags")
+    step = {k: v for k, v in agg.items() if not any(t in k for t in setup)}
+    once = {k: v for k, v in agg.items() if any(t in k for t in setup)}
+    tot = sum(v[1] for v in step.values())
     with open(dst, "w") as f:
         f.write("# per-kernel device time from `ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache,\n"
                 "# serialised launches: compare SHARES with bench.py's kernel_ms_per_step, not absolutes)\n")
-        f.write("# source: %s ; %d launches, %.3f ms total\n" % (src, sum(v[0] for v in agg.values()), tot * scale))
+        f.write("# source: %s ; %d launches of the proof steps, %.3f ms total\n" % (src, sum(v[0] for v in step.values()), tot * scale))
         f.write("%-64s %8s %12s %7s\n" % ("kernel", "launches", "total_ms", "share"))
-        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        for k, v in sorted(step.items(), key=lambda kv: -kv[1][1]):
             f.write("%-64s %8d %12.3f %6.1f%%\n" % (k[:64], v[0], v[1] * scale, 100 * v[1] / tot))
+        f.write("\n# key setup, once per proving key, outside the timed region (%d launches, %.1f ms)\n"
+                % (sum(v[0] for v in once.values()), sum(v[1] for v in once.values()) * scale))
+        for k, v in sorted(once.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-64s %8d %12.3f\n" % (k[:64], v[0], v[1] * scale))
 
 
 def kernel(rep, dst, json_out=None):

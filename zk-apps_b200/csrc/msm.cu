@@ -1307,7 +1307,10 @@ int msm_device(b200zk_ctx* ctx, const b200zk_bases* h, const uint32_t* d_scalars
     uint32_t parts = 1;
     if (!pl.precomp && batch == 1 && slot == 0 && ctx->concurrency) {
         if (ctx->msm_parts) parts = (uint32_t)ctx->msm_parts;
-        else if (n >= (1u << 23)) parts = 4;   // measured (profiles/r01_msm_parts_sweep.log): +2 % at 2^24, a loss below 2^22
+        // measured (profiles/r01_msm_parts_sweep.log): +2 % at 2^24, a loss below 2^22 -- and a loss at every size once
+        // the affine levels run in front of the accumulation (four small level pipelines instead of one that fills
+        // the machine: 2^23 points 60 vs 50 ms, profiles/r02_bench_n2.json), so only without them
+        else if (n >= (1u << 23) && ctx->msm_affine_levels == 0) parts = 4;
     }
     parts = std::min(parts, pl.windows);
     const XYZZ<F>* sums = nullptr;
