@@ -454,6 +454,29 @@ def extras_single_gpu(ctx, z, hbm_peak):
     out["g1_msm_2p24_precompute_once_s"] = pre_s
     h_pre.free()
     del ss_t
+    # ---- the plain `VariableBaseMSM::msm_bigint` call site END TO END at 2^22: bases and scalars in (pageable) host
+    # memory, b200zk_msm_g1 uploads them (0.5 GB H2D), runs the MSM and returns the affine point -- the cost a caller
+    # without resident bases pays (ADVICE / VERDICT r1: no such number existed)
+    lg = 22
+    n = 1 << lg
+    ks_t = rand_scalars_device(torch, n, 79, dev)
+    dpts = ctx.alloc(n * 96)
+    ctx.check(z.lib().b200zk_fixed_base_mul_device(ctx.handle, 1, ks_t.data_ptr(), n, dpts))
+    pts_host = ctx.download(dpts, n * 96)
+    ctx.free(dpts)
+    ss_t = rand_scalars_device(torch, n, 80, dev)
+    want_scalar = dot_mod_r_torch(ss_t, ks_t, z.ffi.R_MOD)
+    ss_host = ss_t.cpu().numpy().reshape(-1)
+    del ks_t, ss_t
+    torch.cuda.empty_cache()
+    z.VariableBaseMSM.msm_bigint(ctx, 1, pts_host, ss_host)
+    t0 = time.perf_counter()
+    got, _ = z.VariableBaseMSM.msm_bigint(ctx, 1, pts_host, ss_host)
+    out["g1_msm_2p22_host_call_ms"] = (time.perf_counter() - t0) * 1e3
+    out["g1_msm_2p22_host_call_h2d_bytes"] = n * (96 + 32)
+    want = ctx.fixed_base_mul(1, np.frombuffer(want_scalar.to_bytes(32, "little"), dtype=np.uint8)).tobytes()
+    out["g1_msm_2p22_host_call_identity_ok"] = bool(bytes(got) == want)
+    assert out["g1_msm_2p22_host_call_identity_ok"], "b200zk_msm_g1 2^22 (host buffers) differs from (sum s_i k_i) * G"
     return out
 
 

@@ -292,3 +292,40 @@ def test_plain_bases_affine_levels(ctx, group, n, c, glv, monkeypatch):
         ctx.set_option("msm_glv", 1); ctx.set_option("msm_affine_levels", 4)
         ctx.set_option("msm_affine_min_entries", 1 << 22); ctx.set_option("msm_affine_b", 96)
         h.free()
+
+
+def test_adversarial_distributions_2p20(ctx):
+    """The skewed cases at n = 2^20: all-equal scalars put every point of a window into ONE bucket, 0/1
+    scalars put half of them into bucket 1 of window 0.  Results against (sum s_i k_i) * G; the wall time of each case is
+    printed next to the uniform one (pytest -s) -- the oversized buckets are summed by runs in parallel and folded by
+    msm_fold_big, so they must stay within a small factor of the uniform time."""
+    import time
+    n = 1 << 20
+    ks = util.rand_fr_bytes_fast(2020, n)
+    pts = ctx.fixed_base_mul(1, ks)
+    kv = ks.reshape(n, 32)
+    # sum k_i mod r without Python big-int loops: limb-wise column sums
+    cols = [int(kv[:, j].astype(np.uint64).sum()) for j in range(32)]
+    ksum = sum(c << (8 * j) for j, c in enumerate(cols)) % R
+    h = z.VariableBaseMSM.Bases(ctx, 1, pts)
+    uni = util.rand_fr_bytes_fast(2021, n)
+    h.msm(uni, n=n)
+    t0 = time.perf_counter(); h.msm(uni, n=n); t_uni = time.perf_counter() - t0
+    times = {}
+    for name, s in (("all_equal_small", 0x1234567), ("all_equal_r_minus_1", R - 1), ("all_equal_254bit", (1 << 254) + 12345)):
+        sc = np.tile(np.frombuffer((s % R).to_bytes(32, "little"), dtype=np.uint8), n)
+        h.msm(sc, n=n)
+        t0 = time.perf_counter(); out, _ = h.msm(sc, n=n); times[name] = time.perf_counter() - t0
+        want = ctx.fixed_base_mul(1, np.frombuffer((ksum * s % R).to_bytes(32, "little"), dtype=np.uint8))
+        assert bytes(out) == bytes(want), name
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2, size=n, dtype=np.uint8)
+    sc = np.zeros((n, 32), dtype=np.uint8); sc[:, 0] = bits
+    h.msm(sc.reshape(-1), n=n)
+    t0 = time.perf_counter(); out, _ = h.msm(sc.reshape(-1), n=n); times["zero_one"] = time.perf_counter() - t0
+    sel = kv[bits == 1]
+    cols = [int(sel[:, j].astype(np.uint64).sum()) for j in range(32)]
+    want = ctx.fixed_base_mul(1, np.frombuffer((sum(c << (8 * j) for j, c in enumerate(cols)) % R).to_bytes(32, "little"), dtype=np.uint8))
+    assert bytes(out) == bytes(want)
+    print("\nG1 MSM 2^20: uniform %.2f ms; " % (t_uni * 1e3) + ", ".join("%s %.2f ms" % (k, v * 1e3) for k, v in times.items()))
+    h.free()
