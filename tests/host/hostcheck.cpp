@@ -24,7 +24,7 @@ template <class F> static void field_op(int op, const uint8_t* a, const uint8_t*
             case 3: r = fp_sqr(x); break;
             case 4: r = fp_inv(x); break;
             case 8: if constexpr (sizeof(F) == sizeof(Fq2)) r = fp_inv(x); else r = fp_inv_uniform(x); break;  // groundwork: branch-uniform inversion
-            case 9: if constexpr (sizeof(F) == sizeof(Fq2)) r = fp_inv(x); else r = fp_inv_safegcd(x); break;  // one-per-warp inversion of msm_affine.cuh
+            case 9: if constexpr (sizeof(F) == sizeof(Fq2)) r = fp_inv(x); else r = fp_inv_binary(x); break;  // the binary Euclid (fp_inv itself is the safegcd inversion)
             default: r = x;
         }
         memcpy(out + i * sizeof(F), &r, sizeof(F));

@@ -183,7 +183,7 @@ def test_host_field_ops(hc, field):
         ops = {0: lambda x, y: (x + y) % mod, 1: lambda x, y: (x - y) % mod, 2: lambda x, y: x * y % mod,
                3: lambda x, y: x * x % mod, 4: lambda x, y: pow(x, -1, mod) if x else 0,
                8: lambda x, y: pow(x, -1, mod) if x else 0,                  # op 8 = fp_inv_uniform (groundwork)
-               9: lambda x, y: pow(x, -1, mod) if x else 0}                  # op 9 = fp_inv_safegcd (msm_affine.cuh)
+               9: lambda x, y: pow(x, -1, mod) if x else 0}                  # op 9 = fp_inv_binary (op 4 = fp_inv = safegcd)
     else:
         A = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(n)] + [(0, 0), (1, 0), (0, 1), (P - 1, P - 1)]
         B = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(n)] + [(P - 1, 1), (P - 1, P - 1), (0, P - 1), (P - 1, P - 1)]

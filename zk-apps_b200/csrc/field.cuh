@@ -383,6 +383,12 @@ HD Fp<C> fp_inv_fermat(const Fp<C>& a) {
     return fp_pow(a, e, C::N);
 }
 
+// fp_inv = the safegcd inversion below (fp_inv_safegcd: a quarter of the instructions of the bit-by-bit Euclid, so the
+// to-affine tails of every MSM, the proof assembly and the final exponentiation wait a quarter as long); the binary
+// Euclid is kept as fp_inv_binary, the independent implementation the host tests compare it with.
+template <class C> HD Fp<C> fp_inv_safegcd(const Fp<C>& a);
+template <class C> HD Fp<C> fp_inv(const Fp<C>& a) { return fp_inv_safegcd(a); }
+
 // Inversion by the binary extended Euclidean algorithm (Guide to ECC, Alg. 2.22): shifts, additions and
 // subtractions only -- roughly a tenth of the instructions of a^(p-2) and none of them on the multiply pipe,
 // which matters because every inversion here sits on a latency-bound tail (to-affine at the end of an MSM,
@@ -390,7 +396,7 @@ HD Fp<C> fp_inv_fermat(const Fp<C>& a) {
 // values).  Invariants: x1 * a = u, x2 * a = v (mod p) on the plain integers; for the Montgomery word aR this
 // yields (aR)^-1 = a^-1 R^-1, and two products by R^2 return a^-1 R.  Returns 0 for a == 0.
 template <class C>
-HD Fp<C> fp_inv(const Fp<C>& a) {
+HD Fp<C> fp_inv_binary(const Fp<C>& a) {
     constexpr int N = C::N;
     uint32_t u[N], v[N];
     Fp<C> x1 = Fp<C>::zero(), x2 = Fp<C>::zero();
